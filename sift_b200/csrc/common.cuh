@@ -1,0 +1,103 @@
+// Shared declarations of the sm_100a kernels behind include/sift_gpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace siftgpu {
+
+constexpr int kMaxOctaves = 12;
+constexpr int kMaxGauss = 12;   // dogs_per_epoch + 1
+constexpr int kMaxRadius = 255; // taps per blur = 2r+1 <= 511
+constexpr int kDescLen = 128;
+constexpr int kRegion = 8;      // reference sift.cpp:61,164
+
+// One emitted extremum (reference sift.cpp:373), canonical (octave, index, x, y) order.
+struct Cand {
+    uint16_t x, y;
+    uint8_t octave, index, filtered, pad;
+};
+static_assert(sizeof(Cand) == 8, "Cand");
+
+// Unfiltered candidate after _eliminateEdgeResponses; `canon` = position in the canonical list.
+struct Surv {
+    uint32_t canon;
+    uint16_t x, y;
+    uint8_t octave, index;
+    uint16_t pad;
+};
+static_assert(sizeof(Surv) == 12, "Surv");
+
+// Keypoint handed to the orientation/descriptor kernels, in the reference's vector order.
+struct KeyIn {
+    uint16_t x, y;
+    uint8_t octave, index;
+    uint8_t tgt;   // slot of the nearest-Gaussian level (_findNearestGaussian, sift.cpp:205-218)
+    uint8_t pad;
+};
+static_assert(sizeof(KeyIn) == 8, "KeyIn");
+
+// A pyramid level as the kernels see it: image b lives at base + b*stride.
+struct LevelRef {
+    float* base;
+    size_t stride; // elements between consecutive images of the batch
+    int w, h;
+};
+
+// One (octave, middle DoG layer) of the extrema scan.
+struct ScanLayer {
+    const float* d0; // below, current, above (image 0 of the batch)
+    const float* d1;
+    const float* d2;
+    size_t stride;       // elements between images
+    int w, h;
+    int n_yw;            // ceil(h/32) mask words per column
+    uint32_t mask_off;   // word offset of this layer inside one image's mask block
+    uint32_t col_base;   // first global column id of this layer
+    uint8_t octave, index;
+};
+
+struct BlurArgs {
+    const float* src;
+    float* dst;      // blurred image (may be null when only the DoG is wanted)
+    float* dog;      // 128 + (dst - src), or null
+    size_t src_stride, dst_stride, dog_stride; // per-image strides (elements)
+    int w, h;
+    const float* taps; // 2r+1 taps, device memory
+    int r;
+};
+
+#define SIFT_CUDA_TRY(expr)                                         \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return siftgpu::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+// ---- launchers (each returns 0 or SIFT_GPU_E_CUDA; they count their launches in *launches) ----
+int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t* launches);
+int launch_resize_nn(const float* src, size_t src_stride, int sw, int sh, float* dst, size_t dst_stride, int dw, int dh,
+                     const int* map_x, const int* map_y, int batch, cudaStream_t s, uint64_t* launches);
+int launch_u8_to_f32(const uint8_t* src, size_t src_stride, float* dst, size_t dst_stride, size_t n, int batch,
+                     cudaStream_t s, uint64_t* launches);
+
+int launch_extrema(const ScanLayer* layers_dev, const ScanLayer* layers_host, int n_layers, int total_cols,
+                   uint32_t mask_words_per_image, uint32_t* mask, uint32_t* col_count, uint32_t* col_off,
+                   Cand* cands, size_t cand_stride, uint32_t* n_cand, int batch, cudaStream_t s, uint64_t* launches);
+
+int launch_eliminate(const ScanLayer* layers_dev, int n_layers, Cand* cands, size_t cand_stride,
+                     const uint32_t* n_cand, Surv* survivors, size_t surv_stride, uint32_t* n_surv, int dogs_per_epoch,
+                     int batch, cudaStream_t s, uint64_t* launches);
+
+// weight tables: blur(level, 1.6f) top-left 16x16 of every (image, target slot)
+int launch_weight_tables(const LevelRef* targets_dev, int n_targets, const float* taps16, int r16, float* tables,
+                         bool fma, int batch, cudaStream_t s, uint64_t* launches);
+// keys of all images concatenated; key_img[i] = image of key i; key_first[b] = first key of image b
+int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* keys, const uint32_t* key_img,
+                       uint32_t n_keys, float* orientation, uint32_t* n_peaks, float* peaks, cudaStream_t s,
+                       uint64_t* launches);
+int launch_descriptors(const LevelRef* targets_dev, int n_targets, const float* tables, const KeyIn* keys,
+                       const uint32_t* key_img, const uint32_t* key_first, uint32_t n_keys, const float* orientation,
+                       float* desc, cudaStream_t s, uint64_t* launches);
+
+}  // namespace siftgpu

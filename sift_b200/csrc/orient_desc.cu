@@ -1,0 +1,299 @@
+// Orientation assignment and descriptors, one warp per keypoint.
+//
+// Orientation (reference sift.cpp:163-203, :220-286; algorithms.cpp:108-133, :153-178):
+//   gradient magnitude (f32 differences, sqrt in double) and orientation (atan2f radians, +360 in
+//   f32, fmod 360) of the nearest Gaussian level G*, 16x16 window, 36 bins
+//   bins[(u16)floorf(o/10) % 35] += mag * G*, accumulated in the reference's x-outer / y-inner order
+//   (one lane per bin walks the samples in that order, so every bin's fp32 sum is sequential);
+//   peak logic and the rank-deficient least-squares parabola exactly as written.
+// Descriptors (sift.cpp:60-128; algorithms.cpp:135-150, :210-223): the reference adds
+//   p.orientation to the orientation pyramid and the top-left 16x16 of blur(G*, 1.6) to the
+//   magnitude pyramid IN PLACE for every keypoint in vector order, so a keypoint sees the
+//   accumulated contributions of every earlier keypoint whose window overlaps its own.  Each warp
+//   replays, in vector order, the earlier keypoints of the same level that overlap its window, then
+//   its own contribution, bins with (u16)floorf(o/45) % 7 and L1-normalises each 4x4 cell.
+#include "common.cuh"
+#include "vigra_qr.cuh"
+
+namespace siftgpu {
+
+constexpr int kWin = 2 * kRegion;  // 16
+
+// alg::gradientMagnitude / gradientOrientation at interior pixel (x, y); 0 on the 1-px border
+// (the pyramids are zero-initialised and only the interior is filled, sift.cpp:137-138).
+__device__ __forceinline__ void gradient_at(const float* __restrict__ G, int w, int h, int x, int y, float* mag,
+                                            float* ori) {
+    if (x < 1 || y < 1 || x > w - 2 || y > h - 2) {
+        *mag = 0.0f;
+        *ori = 0.0f;
+        return;
+    }
+    const float dx = G[(size_t)y * w + x + 1] - G[(size_t)y * w + x - 1];
+    const float dy = G[(size_t)(y + 1) * w + x] - G[(size_t)(y - 1) * w + x];
+    *mag = (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+    const float r = atan2f(dy, dx);
+    const float s = r + 360.0f;
+    *ori = (float)fmod((double)s, 360.0);
+}
+
+// alg::vertexParabola (algorithms.cpp:153-178).
+__device__ float vertex_parabola(int lx, float ly, int px, float py, int rx, float ry) {
+    float a[9], b[3], res[3] = {0.0f, 0.0f, 0.0f};
+    a[0] = (float)((double)lx * (double)lx); a[1] = (float)lx; a[2] = 0.0f;
+    a[3] = (float)((double)px * (double)px); a[4] = (float)px; a[5] = 0.0f;
+    a[6] = (float)((double)rx * (double)rx); a[7] = (float)rx; a[8] = 0.0f;
+    b[0] = ly; b[1] = py; b[2] = ry;
+    qr::solve3(a, b, res);
+    return -res[1] / (2 * res[0]);
+}
+
+// Sift::_findPeaks (sift.cpp:220-286).  Emulates std::set<float>: sorted, unique; a NaN is only
+// ever kept when it is the first value inserted, and then nothing else is.
+__device__ int find_peaks(const float* histo, float* out) {
+    float p[36];
+    int max_index = 0;
+    for (int i = 0; i < 36; ++i) p[i] = histo[i];
+    for (int i = 1; i < 36; ++i)
+        if (p[max_index] < p[i]) max_index = i;  // std::max_element: first of the largest
+    const float range = (float)((double)histo[max_index] * 0.8);
+    for (int i = 0; i < 36; ++i)
+        if (p[i] < range) p[i] = -1.0f;
+    for (int i = 1; i < 35; ++i)
+        if (p[i] < p[i - 1] || p[i] < p[i + 1]) p[i] = -1.0f;
+    int n = 0;
+    bool nan_first = false;
+    for (int pass = 0; pass < 37; ++pass) {
+        int i;
+        if (pass == 0) i = max_index;
+        else {
+            i = pass - 1;
+            if (!(p[i] > -1.0f) || i == max_index) continue;
+        }
+        int lx, rx;
+        float ly, ry;
+        if (i == 0) { lx = 35 * 10 + 5; ly = histo[35]; } else { lx = (i - 1) * 10 + 5; ly = histo[i - 1]; }
+        if (i == 35) { rx = 5; ry = histo[0]; } else { rx = (i + 1) * 10 + 5; ry = histo[i + 1]; }
+        const float v = vertex_parabola(lx, ly, i * 10 + 5, histo[i], rx, ry);
+        if (pass == 0) {
+            out[n++] = v;
+            nan_first = (v != v);
+            continue;
+        }
+        if (nan_first || v != v) continue;
+        int pos = 0;
+        bool dup = false;
+        while (pos < n && out[pos] < v) ++pos;
+        if (pos < n && out[pos] == v) dup = true;
+        if (dup) continue;
+        for (int k = n; k > pos; --k) out[k] = out[k - 1];
+        out[pos] = v;
+        ++n;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(128) orientation_kernel(const LevelRef* __restrict__ targets, const KeyIn* __restrict__ keys,
+                                                          const uint32_t* __restrict__ key_img, uint32_t n_keys,
+                                                          float* __restrict__ orientation, uint32_t* __restrict__ n_peaks,
+                                                          float* __restrict__ peaks) {
+    __shared__ float s_val[4][kWin * kWin];
+    __shared__ uint16_t s_bin[4][kWin * kWin];
+    __shared__ float s_hist[4][36];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_keys; k += warps) {
+        const KeyIn key = keys[k];
+        const LevelRef T = targets[key.tgt];
+        const float* G = T.base + (size_t)key_img[k] * T.stride;
+        const int x0 = key.x - kRegion, y0 = key.y - kRegion;
+        // sample s = wx*16 + wy is the reference's (x outer, y inner) visiting order
+        for (int s = lane; s < kWin * kWin; s += 32) {
+            const int wx = s >> 4, wy = s & 15;
+            float mag, ori;
+            gradient_at(G, T.w, T.h, x0 + wx, y0 + wy, &mag, &ori);
+            const float g = G[(size_t)(y0 + wy) * T.w + x0 + wx];
+            s_val[wib][s] = mag * g;
+            uint16_t bi = (uint16_t)(int)floorf(ori / 10);
+            s_bin[wib][s] = bi % 35;
+        }
+        __syncwarp();
+        for (int bin = lane; bin < 36; bin += 32) {
+            float acc = 0.0f;
+            for (int s = 0; s < kWin * kWin; ++s)
+                if (s_bin[wib][s] == bin) acc = acc + s_val[wib][s];
+            s_hist[wib][bin] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float out[36];
+            const int n = find_peaks(s_hist[wib], out);
+            orientation[k] = out[0];
+            n_peaks[k] = (uint32_t)n;
+            if (n > 1)
+                for (int i = 0; i < n; ++i) peaks[(size_t)k * 36 + i] = out[i];
+        }
+        __syncwarp();
+    }
+}
+
+// blur(level, 1.6f) evaluated on [0,16)^2 only (the part sift.cpp:88-92 reads).
+template <bool FMA>
+__global__ void __launch_bounds__(256) weight_table_kernel(const LevelRef* __restrict__ targets, const float* __restrict__ taps,
+                                                           int r, float* __restrict__ tables, int n_targets) {
+    extern __shared__ float s_tmp[];  // rows 0..(15+r) x 16
+    const int t = blockIdx.x, b = blockIdx.y;
+    const LevelRef T = targets[t];
+    const float* G = T.base + (size_t)b * T.stride;
+    const int rows = (kWin + r) < T.h ? (kWin + r) : T.h;
+    auto refl = [](int v, int n) { if (v < 0) v = -v; if (v >= n) v = 2 * (n - 1) - v; return v; };
+    for (int i = threadIdx.x; i < rows * kWin; i += blockDim.x) {
+        const int y = i / kWin, x = i - y * kWin;
+        float sum = 0.0f;
+        if (x < T.w)
+            for (int j = 0; j <= 2 * r; ++j) {
+                const float v = G[(size_t)y * T.w + refl(x + j - r, T.w)];
+                sum = FMA ? fmaf(taps[2 * r - j], v, sum) : __fadd_rn(sum, __fmul_rn(taps[2 * r - j], v));
+            }
+        s_tmp[i] = sum;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWin * kWin; i += blockDim.x) {
+        const int y = i / kWin, x = i - y * kWin;
+        float sum = 0.0f;
+        if (x < T.w && y < T.h)
+            for (int j = 0; j <= 2 * r; ++j) {
+                const float v = s_tmp[refl(y + j - r, T.h) * kWin + x];
+                sum = FMA ? fmaf(taps[2 * r - j], v, sum) : __fadd_rn(sum, __fmul_rn(taps[2 * r - j], v));
+            }
+        tables[((size_t)b * n_targets + t) * (kWin * kWin) + y * kWin + x] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restrict__ targets, int n_targets,
+                                                         const float* __restrict__ tables, const KeyIn* __restrict__ keys,
+                                                         const uint32_t* __restrict__ key_img,
+                                                         const uint32_t* __restrict__ key_first, uint32_t n_keys,
+                                                         const float* __restrict__ orientation, float* __restrict__ desc) {
+    __shared__ float s_val[4][kWin * kWin];
+    __shared__ uint16_t s_bin[4][kWin * kWin];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_keys; k += warps) {
+        const KeyIn key = keys[k];
+        const uint32_t img = key_img[k];
+        const LevelRef T = targets[key.tgt];
+        const float* G = T.base + (size_t)img * T.stride;
+        const float* W = tables + ((size_t)img * n_targets + key.tgt) * (kWin * kWin);  // W[y*16 + x]
+        const int x0 = key.x - kRegion, y0 = key.y - kRegion;
+
+        // lane owns window pixels s = lane + 32*j, s = wx*16 + wy
+        float O[8], M[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int s = lane + 32 * j, wx = s >> 4, wy = s & 15;
+            gradient_at(G, T.w, T.h, x0 + wx, y0 + wy, &M[j], &O[j]);
+        }
+        // replay earlier keypoints of this image and level whose window overlaps, in vector order
+        const uint32_t first = key_first[img];
+        for (uint32_t base = first; base < k; base += 32) {
+            const uint32_t m = base + lane;
+            bool hit = false;
+            KeyIn km;
+            if (m < k) {
+                km = keys[m];
+                const int ddx = (int)km.x - (int)key.x, ddy = (int)km.y - (int)key.y;
+                hit = km.tgt == key.tgt && ddx > -kWin && ddx < kWin && ddy > -kWin && ddy < kWin;
+            }
+            unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            while (ballot) {
+                const int src = __ffs(ballot) - 1;
+                ballot &= ballot - 1;
+                const int mx0 = __shfl_sync(0xffffffffu, (int)km.x, src) - kRegion;
+                const int my0 = __shfl_sync(0xffffffffu, (int)km.y, src) - kRegion;
+                const float theta = orientation[base + src];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int s = lane + 32 * j, wx = s >> 4, wy = s & 15;
+                    const int lx = x0 + wx - mx0, ly = y0 + wy - my0;  // position inside the earlier window
+                    if (lx >= 0 && lx < kWin && ly >= 0 && ly < kWin) {
+                        O[j] = O[j] + theta;
+                        M[j] = M[j] + W[ly * kWin + lx];
+                    }
+                }
+            }
+        }
+        const float theta = orientation[k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int s = lane + 32 * j, wx = s >> 4, wy = s & 15;
+            O[j] = O[j] + theta;
+            M[j] = M[j] + W[wy * kWin + wx];
+            const float g = G[(size_t)(y0 + wy) * T.w + x0 + wx];
+            s_val[wib][s] = M[j] * g;
+            uint16_t bi = (uint16_t)(int)floorf(O[j] / 45);
+            s_bin[wib][s] = bi % 7;
+        }
+        __syncwarp();
+        // 16 cells (cx outer, cy inner); lanes 0..15 take one cell each
+        if (lane < 16) {
+            const int cx = (lane >> 2) * 4, cy = (lane & 3) * 4;
+            float bins[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) bins[q] = 0.0f;
+            for (int x = 0; x < 4; ++x)
+                for (int y = 0; y < 4; ++y) {
+                    const int s = (cx + x) * kWin + cy + y;
+                    const int bi = s_bin[wib][s];
+                    const float v = s_val[wib][s];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q == bi) bins[q] = bins[q] + v;
+                }
+            float length = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) length = length + bins[q];
+            float* out = desc + (size_t)k * kDescLen + lane * 8;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) out[q] = (length == 0.0f) ? bins[q] : bins[q] / length;
+        }
+        __syncwarp();
+    }
+}
+
+int launch_weight_tables(const LevelRef* targets_dev, int n_targets, const float* taps16, int r16, float* tables,
+                         bool fma, int batch, cudaStream_t s, uint64_t* launches) {
+    dim3 grid(n_targets, batch);
+    const size_t smem = sizeof(float) * (size_t)(kWin + r16) * kWin;
+    if (fma) weight_table_kernel<true><<<grid, 256, smem, s>>>(targets_dev, taps16, r16, tables, n_targets);
+    else weight_table_kernel<false><<<grid, 256, smem, s>>>(targets_dev, taps16, r16, tables, n_targets);
+    if (launches) ++*launches;
+    SIFT_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* keys, const uint32_t* key_img,
+                       uint32_t n_keys, float* orientation, uint32_t* n_peaks, float* peaks, cudaStream_t s,
+                       uint64_t* launches) {
+    (void)n_targets;
+    if (n_keys == 0) return 0;
+    const unsigned blocks = (unsigned)((n_keys + 3) / 4);
+    orientation_kernel<<<blocks < 148u * 8u ? blocks : 148u * 8u, 128, 0, s>>>(targets_dev, keys, key_img, n_keys, orientation,
+                                                                                n_peaks, peaks);
+    if (launches) ++*launches;
+    SIFT_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_descriptors(const LevelRef* targets_dev, int n_targets, const float* tables, const KeyIn* keys,
+                       const uint32_t* key_img, const uint32_t* key_first, uint32_t n_keys, const float* orientation,
+                       float* desc, cudaStream_t s, uint64_t* launches) {
+    if (n_keys == 0) return 0;
+    const unsigned blocks = (unsigned)((n_keys + 3) / 4);
+    descriptor_kernel<<<blocks < 148u * 8u ? blocks : 148u * 8u, 128, 0, s>>>(targets_dev, n_targets, tables, keys, key_img,
+                                                                               key_first, n_keys, orientation, desc);
+    if (launches) ++*launches;
+    SIFT_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace siftgpu

@@ -1,0 +1,1094 @@
+// Host side of libsift_gpu.so: context, pyramid schedule, device-pass orchestration, the host
+// replay of the reference's std::sort ordering, and the C ABI of include/sift_gpu.h.
+//
+// Path replaced: Sift::calculate (reference sift.cpp:19-57) and everything it calls.  There is no
+// CPU fallback: every stage below runs as a CUDA kernel; the only host arithmetic is the Gaussian
+// tap table (Vigra Kernel1D::initGaussian), the resize index maps, the
+// nearest-Gaussian lookup (sift.cpp:205-218) and the std::sort permutation (sift.cpp:37,49).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sift_gpu.h"
+#include "common.cuh"
+
+namespace siftgpu {
+
+static thread_local std::string g_last_error;
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_last_error = buf;
+    return SIFT_GPU_E_CUDA;
+}
+
+// ---- Vigra Kernel1D<float>::initGaussian (reference algorithms.cpp:13-14) -------------
+static std::vector<float> gaussian_taps(float sigma, int* radius_out) {
+    const double std_dev = (double)sigma;
+    std::vector<float> taps;
+    int radius = 0;
+    if (std_dev > 0.0) {
+        const float sf = (float)std_dev;
+        const float s2 = (float)(-0.5 / (double)sf / (double)sf);
+        const float nrm = (float)(0.3989422804014327 / (double)sf);
+        radius = (int)(3.0 * std_dev + 0.5);
+        if (radius == 0) radius = 1;
+        for (float x = -(float)radius; x <= (float)radius; ++x) {
+            const float x2 = x * x;
+            taps.push_back(nrm * expf(x2 * s2));
+        }
+    } else {
+        taps.push_back(1.0f);
+    }
+    float sum = 0.0f;
+    for (float t : taps) sum += t;
+    sum = 1.0f / sum;
+    for (float& t : taps) t = t * sum;
+    *radius_out = radius;
+    return taps;
+}
+
+// ---- Vigra resizeImageNoInterpolation index walk --------------------------------------
+static std::vector<int> resize_index_map(int n_old, int n_new) {
+    std::vector<int> m((size_t)n_new);
+    if (n_new == 1) { m[0] = 0; return m; }
+    const double dx = (double)(n_old - 1) / (double)(n_new - 1);
+    double x = 0.5;
+    for (int i = 0; i < n_new; ++i, x += dx) m[(size_t)i] = (int)x;
+    return m;
+}
+
+// ---- tiny worker pool for the per-image order replay ------------------------------------------------
+class Pool {
+   public:
+    explicit Pool(int n) {
+        for (int i = 0; i < n; ++i) workers.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> g(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : workers) t.join();
+    }
+    void parallel_for(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        if (workers.empty() || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> g(m);
+            job = &fn; next = 0; total = n; pending = n;
+        }
+        cv.notify_all();
+        // the caller helps
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            fn(i);
+            if (pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m); done_cv.notify_all(); }
+        }
+        std::unique_lock<std::mutex> lk(m);
+        done_cv.wait(lk, [this] { return pending.load() == 0; });
+        job = nullptr;
+    }
+
+   private:
+    void loop() {
+        for (;;) {
+            const std::function<void(int)>* j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return stop || (job && next.load() < total); });
+                if (stop) return;
+                j = job;
+            }
+            for (;;) {
+                int i = next.fetch_add(1);
+                if (i >= total) break;
+                (*j)(i);
+                if (pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m); done_cv.notify_all(); }
+            }
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    const std::function<void(int)>* job = nullptr;
+    std::atomic<int> next{0}, pending{0};
+    int total = 0;
+    bool stop = false;
+};
+
+struct BlurSpec {
+    float sigma = 0;
+    int r = 0;
+    size_t tap_off = 0;  // offset into the device tap pool
+};
+
+struct Plan {
+    int in_w = 0, in_h = 0;
+    int ow[kMaxOctaves] = {0}, oh[kMaxOctaves] = {0};
+    int status = SIFT_GPU_OK;
+    std::string why;
+    int* d_maps = nullptr;  // all index maps, one allocation
+    size_t up_mx = 0, up_my = 0;
+    size_t red_mx[kMaxOctaves] = {0}, red_my[kMaxOctaves] = {0};
+    std::vector<ScanLayer> layers_host;
+    ScanLayer* layers_dev = nullptr;
+    int total_cols = 0;
+    uint32_t mask_words = 0;
+    std::vector<LevelRef> targets_host;
+    LevelRef* targets_dev = nullptr;
+    std::vector<int> class_target;  // (octave*dpe + index) -> target slot
+    std::vector<int> target_octave;
+};
+
+}  // namespace siftgpu
+
+using namespace siftgpu;
+
+struct HostImageOut {
+    std::vector<sift_gpu_keypoint> kps;
+    std::vector<uint32_t> key_of;  // for each kp: index into the device key list of its chunk, or ~0u
+};
+
+struct sift_gpu_ctx {
+    sift_gpu_params prm{};
+    int O = 0, D = 0, G = 0;
+    bool fma = false;
+    cudaStream_t stream = nullptr;
+    std::string error;
+
+    // schedule (size independent)
+    float g_scale[kMaxOctaves][kMaxGauss]{};
+    float d_scale[kMaxOctaves][kMaxGauss]{};
+    BlurSpec base_blur, up_blur, w16_blur;
+    BlurSpec chain_blur[kMaxOctaves][kMaxGauss];
+    BlurSpec reduce_blur[kMaxOctaves];
+    float* d_taps = nullptr;
+    int dead_blur_r[kMaxOctaves][kMaxGauss]{};
+
+    // sizing
+    int B = 1;
+    int max_in_w = 0, max_in_h = 0;
+    size_t max_in_px = 0;
+    size_t maxP[kMaxOctaves]{};
+    size_t cand_cap = 0;
+
+    // device buffers
+    uint8_t* d_in_u8 = nullptr;
+    float* d_in = nullptr;
+    float* d_up_tmp = nullptr;  // blur(img, 1.0) at input resolution
+    float* d_up = nullptr;      // 2x image
+    float* d_scratch = nullptr; // full-resolution blur before decimation
+    float* d_gauss[kMaxOctaves][kMaxGauss]{};
+    float* d_dog[kMaxOctaves][kMaxGauss]{};
+    uint32_t* d_mask = nullptr;
+    size_t mask_cap = 0;
+    uint32_t *d_col_count = nullptr, *d_col_off = nullptr;
+    size_t col_cap = 0;
+    Cand* d_cands = nullptr;
+    Surv* d_surv = nullptr;
+    uint32_t *d_n_cand = nullptr, *d_n_surv = nullptr;
+    uint32_t *h_n_cand = nullptr, *h_n_surv = nullptr;  // pinned
+    Surv* h_surv = nullptr;                              // pinned, grows
+    size_t h_surv_cap = 0;
+
+    // keypoint stage buffers (grow on demand)
+    size_t key_cap = 0;
+    KeyIn* d_keys = nullptr; KeyIn* h_keys = nullptr;
+    uint32_t* d_key_img = nullptr; uint32_t* h_key_img = nullptr;
+    uint32_t* d_key_first = nullptr; uint32_t* h_key_first = nullptr;
+    float* d_orient = nullptr; float* h_orient = nullptr;
+    uint32_t* d_npeaks = nullptr; uint32_t* h_npeaks = nullptr;
+    float* d_peaks = nullptr;
+    float* d_desc = nullptr;
+    float* d_tables = nullptr;
+    size_t tables_cap = 0;
+
+    // per-run result storage (pinned descriptor blocks + host vectors)
+    std::vector<float*> desc_blocks;
+    std::vector<size_t> desc_block_cap;
+    size_t desc_blocks_used = 0;
+    std::vector<HostImageOut> outs;
+
+    std::map<std::pair<int, int>, Plan*> plans;
+    Plan* last_plan = nullptr;
+    int last_batch = 0;
+    Pool* pool = nullptr;
+
+    sift_gpu_timings tm{};
+    cudaEvent_t ev[12]{};
+};
+
+static int set_error(sift_gpu_ctx* c, int code, const std::string& msg) {
+    if (c) c->error = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define CTX_TRY(expr)                                       \
+    do {                                                    \
+        int _rc = (expr);                                   \
+        if (_rc != 0) { if (c) c->error = g_last_error; return _rc; } \
+    } while (0)
+#define CTX_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) { int _rc = cuda_fail(_e, #expr, __FILE__, __LINE__); if (c) c->error = g_last_error; return _rc; } \
+    } while (0)
+
+static size_t level_px(int w, int h) { return (size_t)w * (size_t)h; }
+
+// Schedule of Sift::_createDOGs (sift.cpp:381-417): scale labels, radii, taps.
+static int build_schedule(sift_gpu_ctx* c) {
+    const int O = c->O, D = c->D;
+    std::vector<float> pool;
+    auto add = [&](float sigma) {
+        BlurSpec b;
+        b.sigma = sigma;
+        std::vector<float> t = gaussian_taps(sigma, &b.r);
+        while (pool.size() % 4) pool.push_back(0.0f);
+        b.tap_off = pool.size();
+        pool.insert(pool.end(), t.begin(), t.end());
+        return b;
+    };
+    c->base_blur = add(c->prm.sigma);
+    c->up_blur = add(1.0f);     // sift.cpp:21
+    c->w16_blur = add(1.6f);    // sift.cpp:87
+    c->g_scale[0][0] = c->prm.sigma;
+    uint16_t exp = 0;
+    for (int i = 0; i < O; i++) {
+        for (int j = 1; j < D + 1; j++) {
+            const float scale = (float)(std::pow((double)c->prm.k, (double)exp) * (double)c->prm.sigma);
+            c->g_scale[i][j] = scale;
+            c->chain_blur[i][j] = add(scale);
+            c->d_scale[i][j - 1] = c->g_scale[i][j] - c->g_scale[i][j - 1];
+            exp++;
+        }
+        if (i < O - 1) {
+            c->g_scale[i + 1][0] = c->g_scale[i][D - 1];
+            c->reduce_blur[i] = add(c->g_scale[i][D - 1]);
+            exp -= 2;
+        }
+    }
+    for (int e = 0; e < O; ++e)
+        for (int i = 0; i < D; ++i) {
+            int r = 0;
+            (void)gaussian_taps((float)(1.5 * (double)c->d_scale[e][i]), &r);  // sift.cpp:184
+            c->dead_blur_r[e][i] = r;
+        }
+    CTX_CUDA(cudaMalloc(&c->d_taps, sizeof(float) * pool.size()));
+    CTX_CUDA(cudaMemcpy(c->d_taps, pool.data(), sizeof(float) * pool.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static void octave_dims(const sift_gpu_ctx* c, int in_w, int in_h, int* ow, int* oh) {
+    int w = c->prm.subpixel ? in_w * 2 : in_w, h = c->prm.subpixel ? in_h * 2 : in_h;
+    for (int o = 0; o < c->O; ++o) {
+        ow[o] = w; oh[o] = h;
+        w = (w + 1) / 2; h = (h + 1) / 2;
+    }
+}
+
+// Sift::_findNearestGaussian (sift.cpp:205-218).
+static void nearest_gaussian(const sift_gpu_ctx* c, float scale, int* o_out, int* i_out) {
+    float lowest = 100;
+    int bo = 0, bi = 0;
+    for (int o = 0; o < c->O; o++)
+        for (int i = 0; i < c->G; i++) {
+            const float cur = std::abs(c->g_scale[o][i] - scale);
+            if (cur < lowest) { lowest = cur; bo = o; bi = i; }
+        }
+    *o_out = bo; *i_out = bi;
+}
+
+static constexpr int kMaxTileRadius = 80;  // what the generic tile kernel's shared memory holds
+
+static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
+    auto key = std::make_pair(in_w, in_h);
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) return it->second;
+    Plan* p = new Plan();
+    c->plans[key] = p;
+    p->in_w = in_w; p->in_h = in_h;
+    octave_dims(c, in_w, in_h, p->ow, p->oh);
+    const int O = c->O, D = c->D;
+
+    auto fail = [&](int code, const char* why) { if (p->status == SIFT_GPU_OK) { p->status = code; p->why = why; } };
+    auto check_blur = [&](const BlurSpec& b, int w, int h) {
+        if (w < b.r + 1 || h < b.r + 1) fail(SIFT_GPU_E_PRECONDITION, "separableConvolveX/Y(): kernel longer than line");
+        if (b.r > kMaxTileRadius) fail(SIFT_GPU_E_UNSUPPORTED, "blur radius exceeds the tile kernel's shared memory");
+    };
+    if (in_w < 1 || in_h < 1) fail(SIFT_GPU_E_INVALID, "empty image");
+    if (c->prm.subpixel) {
+        check_blur(c->up_blur, in_w, in_h);
+        if (!(in_w > 1 && in_h > 1)) fail(SIFT_GPU_E_PRECONDITION, "resizeImageNoInterpolation(): Source image too small.");
+    }
+    check_blur(c->base_blur, p->ow[0], p->oh[0]);
+    for (int o = 0; o < O; ++o) {
+        for (int j = 1; j <= D; ++j) check_blur(c->chain_blur[o][j], p->ow[o], p->oh[o]);
+        if (o < O - 1) {
+            check_blur(c->reduce_blur[o], p->ow[o], p->oh[o]);
+            if (!(p->ow[o] > 1 && p->oh[o] > 1)) fail(SIFT_GPU_E_PRECONDITION, "resizeImageNoInterpolation(): Source image too small.");
+            if (!(p->ow[o + 1] > 1 && p->oh[o + 1] > 1)) fail(SIFT_GPU_E_PRECONDITION, "resizeImageNoInterpolation(): Destination image too small.");
+        }
+    }
+    if (p->status != SIFT_GPU_OK) return p;
+
+    // index maps
+    std::vector<int> maps;
+    auto push_map = [&](int n_old, int n_new) {
+        size_t off = maps.size();
+        std::vector<int> m = resize_index_map(n_old, n_new);
+        maps.insert(maps.end(), m.begin(), m.end());
+        return off;
+    };
+    if (c->prm.subpixel) { p->up_mx = push_map(in_w, in_w * 2); p->up_my = push_map(in_h, in_h * 2); }
+    for (int o = 0; o + 1 < O; ++o) { p->red_mx[o] = push_map(p->ow[o], p->ow[o + 1]); p->red_my[o] = push_map(p->oh[o], p->oh[o + 1]); }
+    if (!maps.empty()) {
+        if (cudaMalloc(&p->d_maps, sizeof(int) * maps.size()) != cudaSuccess ||
+            cudaMemcpy(p->d_maps, maps.data(), sizeof(int) * maps.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            fail(SIFT_GPU_E_CUDA, "index map upload failed");
+            return p;
+        }
+    }
+    // extrema scan layers, ordered (octave, index)
+    uint32_t mask_off = 0, col_base = 0;
+    for (int e = 0; e < O; ++e)
+        for (int i = 1; i < D - 1; ++i) {
+            ScanLayer L{};
+            L.d0 = c->d_dog[e][i - 1]; L.d1 = c->d_dog[e][i]; L.d2 = c->d_dog[e][i + 1];
+            L.stride = c->maxP[e];
+            L.w = p->ow[e]; L.h = p->oh[e];
+            L.n_yw = (L.h + 31) / 32;
+            L.mask_off = mask_off; L.col_base = col_base;
+            L.octave = (uint8_t)e; L.index = (uint8_t)i;
+            mask_off += (uint32_t)L.n_yw * (uint32_t)L.w;
+            col_base += (uint32_t)L.w;
+            p->layers_host.push_back(L);
+        }
+    p->mask_words = mask_off;
+    p->total_cols = (int)col_base;
+    // nearest-Gaussian targets per keypoint class
+    p->class_target.assign((size_t)(O * D), -1);
+    for (int e = 0; e < O; ++e)
+        for (int i = 1; i < D - 1; ++i) {
+            int to, ti;
+            nearest_gaussian(c, c->d_scale[e][i], &to, &ti);
+            int slot = -1;
+            for (size_t s = 0; s < p->targets_host.size(); ++s)
+                if (p->targets_host[s].base == c->d_gauss[to][ti]) slot = (int)s;
+            if (slot < 0) {
+                slot = (int)p->targets_host.size();
+                p->targets_host.push_back(LevelRef{c->d_gauss[to][ti], c->maxP[to], p->ow[to], p->oh[to]});
+                p->target_octave.push_back(to);
+            }
+            p->class_target[(size_t)(e * D + i)] = slot;
+        }
+    if (cudaMalloc(&p->layers_dev, sizeof(ScanLayer) * p->layers_host.size()) != cudaSuccess ||
+        cudaMemcpy(p->layers_dev, p->layers_host.data(), sizeof(ScanLayer) * p->layers_host.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&p->targets_dev, sizeof(LevelRef) * p->targets_host.size()) != cudaSuccess ||
+        cudaMemcpy(p->targets_dev, p->targets_host.data(), sizeof(LevelRef) * p->targets_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+        fail(SIFT_GPU_E_CUDA, "plan upload failed");
+    return p;
+}
+
+static int alloc_buffers(sift_gpu_ctx* c) {
+    const int O = c->O, D = c->D, B = c->B;
+    int ow[kMaxOctaves], oh[kMaxOctaves];
+    octave_dims(c, c->max_in_w, c->max_in_h, ow, oh);
+    c->max_in_px = level_px(c->max_in_w, c->max_in_h);
+    size_t cand_cap = 0, mask_cap = 0, col_cap = 0;
+    for (int o = 0; o < O; ++o) {
+        c->maxP[o] = level_px(ow[o], oh[o]);
+        cand_cap += c->maxP[o] * (size_t)(D - 2);
+        mask_cap += (size_t)((oh[o] + 31) / 32 + 1) * (size_t)ow[o] * (size_t)(D - 2);
+        col_cap += (size_t)ow[o] * (size_t)(D - 2);
+    }
+    c->cand_cap = cand_cap; c->mask_cap = mask_cap; c->col_cap = col_cap;
+    CTX_CUDA(cudaMalloc(&c->d_in_u8, c->max_in_px * (size_t)B));
+    CTX_CUDA(cudaMalloc(&c->d_in, sizeof(float) * c->max_in_px * (size_t)B));
+    if (c->prm.subpixel) {
+        CTX_CUDA(cudaMalloc(&c->d_up_tmp, sizeof(float) * c->max_in_px * (size_t)B));
+        CTX_CUDA(cudaMalloc(&c->d_up, sizeof(float) * c->maxP[0] * (size_t)B));
+    }
+    CTX_CUDA(cudaMalloc(&c->d_scratch, sizeof(float) * c->maxP[0] * (size_t)B));
+    for (int o = 0; o < O; ++o) {
+        for (int i = 0; i <= D; ++i) CTX_CUDA(cudaMalloc(&c->d_gauss[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
+        for (int i = 0; i < D; ++i) CTX_CUDA(cudaMalloc(&c->d_dog[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
+    }
+    CTX_CUDA(cudaMalloc(&c->d_mask, sizeof(uint32_t) * mask_cap * (size_t)B));
+    CTX_CUDA(cudaMalloc(&c->d_col_count, sizeof(uint32_t) * col_cap * (size_t)B));
+    CTX_CUDA(cudaMalloc(&c->d_col_off, sizeof(uint32_t) * col_cap * (size_t)B));
+    CTX_CUDA(cudaMalloc(&c->d_cands, sizeof(Cand) * cand_cap * (size_t)B));
+    CTX_CUDA(cudaMalloc(&c->d_surv, sizeof(Surv) * cand_cap * (size_t)B));
+    CTX_CUDA(cudaMalloc(&c->d_n_cand, sizeof(uint32_t) * (size_t)B));
+    CTX_CUDA(cudaMalloc(&c->d_n_surv, sizeof(uint32_t) * (size_t)B));
+    CTX_CUDA(cudaHostAlloc(&c->h_n_cand, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
+    CTX_CUDA(cudaHostAlloc(&c->h_n_surv, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
+    CTX_CUDA(cudaMalloc(&c->d_key_first, sizeof(uint32_t) * (size_t)(B + 1)));
+    CTX_CUDA(cudaHostAlloc(&c->h_key_first, sizeof(uint32_t) * (size_t)(B + 1), cudaHostAllocDefault));
+    return 0;
+}
+
+static int ensure_key_capacity(sift_gpu_ctx* c, size_t n) {
+    if (n <= c->key_cap) return 0;
+    size_t cap = std::max<size_t>(n * 3 / 2, 4096);
+    cudaFree(c->d_keys); cudaFree(c->d_key_img); cudaFree(c->d_orient); cudaFree(c->d_npeaks); cudaFree(c->d_peaks); cudaFree(c->d_desc);
+    cudaFreeHost(c->h_keys); cudaFreeHost(c->h_key_img); cudaFreeHost(c->h_orient); cudaFreeHost(c->h_npeaks);
+    c->key_cap = 0;
+    CTX_CUDA(cudaMalloc(&c->d_keys, sizeof(KeyIn) * cap));
+    CTX_CUDA(cudaMalloc(&c->d_key_img, sizeof(uint32_t) * cap));
+    CTX_CUDA(cudaMalloc(&c->d_orient, sizeof(float) * cap));
+    CTX_CUDA(cudaMalloc(&c->d_npeaks, sizeof(uint32_t) * cap));
+    CTX_CUDA(cudaMalloc(&c->d_peaks, sizeof(float) * 36 * cap));
+    CTX_CUDA(cudaMalloc(&c->d_desc, sizeof(float) * kDescLen * cap));
+    CTX_CUDA(cudaHostAlloc(&c->h_keys, sizeof(KeyIn) * cap, cudaHostAllocDefault));
+    CTX_CUDA(cudaHostAlloc(&c->h_key_img, sizeof(uint32_t) * cap, cudaHostAllocDefault));
+    CTX_CUDA(cudaHostAlloc(&c->h_orient, sizeof(float) * cap, cudaHostAllocDefault));
+    CTX_CUDA(cudaHostAlloc(&c->h_npeaks, sizeof(uint32_t) * cap, cudaHostAllocDefault));
+    c->key_cap = cap;
+    return 0;
+}
+
+static int ensure_surv_capacity(sift_gpu_ctx* c, size_t n) {
+    if (n <= c->h_surv_cap) return 0;
+    size_t cap = std::max<size_t>(n * 3 / 2, 1 << 16);
+    cudaFreeHost(c->h_surv);
+    c->h_surv_cap = 0;
+    CTX_CUDA(cudaHostAlloc(&c->h_surv, sizeof(Surv) * cap, cudaHostAllocDefault));
+    c->h_surv_cap = cap;
+    return 0;
+}
+
+static float* take_desc_block(sift_gpu_ctx* c, size_t floats) {
+    if (floats == 0) floats = 1;
+    if (c->desc_blocks_used < c->desc_blocks.size()) {
+        size_t i = c->desc_blocks_used;
+        if (c->desc_block_cap[i] < floats) {
+            cudaFreeHost(c->desc_blocks[i]);
+            c->desc_blocks[i] = nullptr;
+            size_t cap = floats * 3 / 2;
+            if (cudaHostAlloc(&c->desc_blocks[i], sizeof(float) * cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+            c->desc_block_cap[i] = cap;
+        }
+        ++c->desc_blocks_used;
+        return c->desc_blocks[i];
+    }
+    float* p = nullptr;
+    size_t cap = floats * 3 / 2;
+    if (cudaHostAlloc(&p, sizeof(float) * cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    c->desc_blocks.push_back(p);
+    c->desc_block_cap.push_back(cap);
+    ++c->desc_blocks_used;
+    return p;
+}
+
+// ---- device passes ------------------------------------------------------------------------------
+static BlurArgs blur_args(const sift_gpu_ctx* c, const BlurSpec& b, const float* src, size_t sstride, float* dst,
+                          size_t dstride, float* dog, size_t gstride, int w, int h) {
+    BlurArgs a{};
+    a.src = src; a.dst = dst; a.dog = dog;
+    a.src_stride = sstride; a.dst_stride = dstride; a.dog_stride = gstride;
+    a.w = w; a.h = h; a.taps = c->d_taps + b.tap_off; a.r = b.r;
+    return a;
+}
+
+// Sift::calculate's upsample (sift.cpp:20-21) + _createDOGs (sift.cpp:381-417) for nb images in d_in.
+static int run_pyramid(sift_gpu_ctx* c, const Plan* p, int nb) {
+    const int O = c->O, D = c->D;
+    uint64_t* L = &c->tm.kernel_launches;
+    cudaStream_t s = c->stream;
+    const float* base_src = c->d_in;
+    size_t base_stride = c->max_in_px;
+    if (c->prm.subpixel) {
+        CTX_TRY(launch_blur(blur_args(c, c->up_blur, c->d_in, c->max_in_px, c->d_up_tmp, c->max_in_px, nullptr, 0, p->in_w, p->in_h), nb, c->fma, s, L));
+        CTX_TRY(launch_resize_nn(c->d_up_tmp, c->max_in_px, p->in_w, p->in_h, c->d_up, c->maxP[0], p->ow[0], p->oh[0],
+                                 p->d_maps + p->up_mx, p->d_maps + p->up_my, nb, s, L));
+        base_src = c->d_up;
+        base_stride = c->maxP[0];
+    }
+    CTX_TRY(launch_blur(blur_args(c, c->base_blur, base_src, base_stride, c->d_gauss[0][0], c->maxP[0], nullptr, 0, p->ow[0], p->oh[0]), nb, c->fma, s, L));
+    for (int o = 0; o < O; ++o) {
+        for (int j = 1; j <= D; ++j)
+            CTX_TRY(launch_blur(blur_args(c, c->chain_blur[o][j], c->d_gauss[o][j - 1], c->maxP[o], c->d_gauss[o][j], c->maxP[o],
+                                          c->d_dog[o][j - 1], c->maxP[o], p->ow[o], p->oh[o]), nb, c->fma, s, L));
+        if (o < O - 1) {
+            CTX_TRY(launch_blur(blur_args(c, c->reduce_blur[o], c->d_gauss[o][D - 1], c->maxP[o], c->d_scratch, c->maxP[0], nullptr, 0,
+                                          p->ow[o], p->oh[o]), nb, c->fma, s, L));
+            CTX_TRY(launch_resize_nn(c->d_scratch, c->maxP[0], p->ow[o], p->oh[o], c->d_gauss[o + 1][0], c->maxP[o + 1], p->ow[o + 1],
+                                     p->oh[o + 1], p->d_maps + p->red_mx[o], p->d_maps + p->red_my[o], nb, s, L));
+        }
+    }
+    return 0;
+}
+
+// The reference's cleanup (sift.cpp:37-42): std::sort with cmpByFilter, count of leading unfiltered
+// truncated to u16.  `flags[i]` = filtered; returns the kept source indices in their new order.
+static void cleanup_order(const std::vector<uint8_t>& flags, bool canonical, std::vector<uint32_t>* kept) {
+    const size_t n = flags.size();
+    std::vector<uint32_t> v(n);
+    for (size_t i = 0; i < n; ++i) v[i] = (uint32_t)i | (flags[i] ? 0x80000000u : 0u);
+    if (canonical)
+        std::stable_partition(v.begin(), v.end(), [](uint32_t a) { return !(a >> 31); });
+    else
+        std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
+    size_t unf = 0;
+    while (unf < n && !(v[unf] >> 31)) ++unf;
+    const uint16_t size = (uint16_t)unf;
+    kept->resize(size);
+    for (size_t i = 0; i < size; ++i) (*kept)[i] = v[i] & 0x7fffffffu;
+}
+
+struct ReplayOut {
+    int status = SIFT_GPU_OK;
+    uint32_t n_survivors = 0;
+    std::vector<sift_gpu_keypoint> kps;  // final vector order (orientation/descriptor filled later)
+    std::vector<KeyIn> keys;             // the subset that goes to the device, same order
+    std::vector<uint32_t> key_of;        // kp -> index in keys or ~0u
+};
+
+// Host half of Sift::calculate between _eliminateEdgeResponses and _createDecriptors (sift.cpp:37-55).
+static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, const Surv* surv_in, uint32_t n_surv,
+                         ReplayOut* out) {
+    const bool canonical = (c->prm.flags & SIFT_GPU_FLAG_ORDER_CANONICAL) != 0;
+    const int D = c->D;
+    std::vector<Surv> S(surv_in, surv_in + n_surv);
+    std::sort(S.begin(), S.end(), [](const Surv& a, const Surv& b) { return a.canon < b.canon; });
+    // first cleanup over all candidates
+    std::vector<uint32_t> L1;  // survivor slots in vector order
+    {
+        std::vector<uint32_t> v(n_cand, 0x80000000u);
+        for (uint32_t s = 0; s < n_surv; ++s) v[S[s].canon] = s;
+        if (canonical)
+            std::stable_partition(v.begin(), v.end(), [](uint32_t a) { return !(a >> 31); });
+        else
+            std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
+        const uint16_t size = (uint16_t)n_surv;  // u16_t size = distance(...) (sift.cpp:41)
+        L1.assign(v.begin(), v.begin() + size);
+    }
+    out->n_survivors = (uint32_t)L1.size();
+    // _orientationAssignment bounds test (sift.cpp:173-178) and the dead blur's precondition (sift.cpp:184)
+    std::vector<uint8_t> flags2(L1.size());
+    for (size_t i = 0; i < L1.size(); ++i) {
+        const Surv& s = S[L1[i]];
+        const LevelRef& T = p->targets_host[(size_t)p->class_target[(size_t)(s.octave * D + s.index)]];
+        const bool outside = (s.x < kRegion || s.x >= T.w - kRegion) || (s.y < kRegion || s.y >= T.h - kRegion);
+        flags2[i] = outside ? 1 : 0;
+        if (!outside && (c->prm.flags & SIFT_GPU_FLAG_STRICT) && 2 * kRegion < c->dead_blur_r[s.octave][s.index] + 1) {
+            out->status = SIFT_GPU_E_PRECONDITION;
+            return;
+        }
+    }
+    std::vector<uint32_t> L2;
+    cleanup_order(flags2, canonical, &L2);
+    out->kps.resize(L2.size());
+    out->key_of.assign(L2.size(), ~0u);
+    out->keys.clear();
+    for (size_t i = 0; i < L2.size(); ++i) {
+        const Surv& s = S[L1[L2[i]]];
+        const int slot = p->class_target[(size_t)(s.octave * D + s.index)];
+        const LevelRef& T = p->targets_host[(size_t)slot];
+        sift_gpu_keypoint& k = out->kps[i];
+        k.x = s.x; k.y = s.y; k.octave = s.octave; k.index = s.index;
+        k.scale = c->d_scale[s.octave][s.index];
+        k.orientation = 0.0f;
+        k.reserved = 0;
+        // _createDecriptors bounds test (sift.cpp:65-70)
+        const bool reject = s.x < kRegion || s.x > T.w - kRegion || s.y < kRegion || s.y > T.h - kRegion;
+        k.filtered = reject ? 1 : 0;
+        k.desc_len = reject ? 0 : kDescLen;
+        if (!reject) {
+            out->key_of[i] = (uint32_t)out->keys.size();
+            KeyIn ki;
+            ki.x = s.x; ki.y = s.y; ki.octave = s.octave; ki.index = s.index; ki.tgt = (uint8_t)slot; ki.pad = 0;
+            out->keys.push_back(ki);
+        }
+    }
+}
+
+struct ChunkImage {
+    int result_index;
+    const sift_gpu_image* img;
+};
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int run_chunk(sift_gpu_ctx* c, Plan* p, const std::vector<ChunkImage>& imgs, sift_gpu_result* results) {
+    const int nb = (int)imgs.size();
+    cudaStream_t s = c->stream;
+    uint64_t* L = &c->tm.kernel_launches;
+    const size_t in_px = level_px(p->in_w, p->in_h);
+    c->last_plan = p;
+    c->last_batch = nb;
+
+    CTX_CUDA(cudaEventRecord(c->ev[0], s));
+    // upload (main.cpp:52-54 leaves band 0 as float 0..255; u8 input is widened on the device)
+    for (int b = 0; b < nb; ++b) {
+        const sift_gpu_image& im = *imgs[(size_t)b].img;
+        const size_t esz = im.dtype == SIFT_GPU_DTYPE_U8 ? 1 : 4;
+        const size_t pitch = im.row_stride_bytes ? (size_t)im.row_stride_bytes : (size_t)im.width * esz;
+        void* dst = im.dtype == SIFT_GPU_DTYPE_U8 ? (void*)(c->d_in_u8 + (size_t)b * c->max_in_px)
+                                                  : (void*)(c->d_in + (size_t)b * c->max_in_px);
+        const cudaMemcpyKind kind = im.memory == SIFT_GPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)im.width * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
+    }
+    if (imgs[0].img->dtype == SIFT_GPU_DTYPE_U8)
+        CTX_TRY(launch_u8_to_f32(c->d_in_u8, c->max_in_px, c->d_in, c->max_in_px, in_px, nb, s, L));
+    CTX_CUDA(cudaEventRecord(c->ev[1], s));
+    CTX_TRY(run_pyramid(c, p, nb));
+    CTX_CUDA(cudaEventRecord(c->ev[2], s));
+    CTX_TRY(launch_extrema(p->layers_dev, p->layers_host.data(), (int)p->layers_host.size(), p->total_cols, p->mask_words,
+                           c->d_mask, c->d_col_count, c->d_col_off, c->d_cands, c->cand_cap, c->d_n_cand, nb, s, L));
+    CTX_CUDA(cudaEventRecord(c->ev[3], s));
+    CTX_TRY(launch_eliminate(p->layers_dev, (int)p->layers_host.size(), c->d_cands, c->cand_cap, c->d_n_cand, c->d_surv,
+                             c->cand_cap, c->d_n_surv, c->D, nb, s, L));
+    CTX_CUDA(cudaEventRecord(c->ev[4], s));
+    CTX_CUDA(cudaMemcpyAsync(c->h_n_cand, c->d_n_cand, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(cudaMemcpyAsync(c->h_n_surv, c->d_n_surv, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(cudaStreamSynchronize(s));
+    std::vector<size_t> surv_off((size_t)nb + 1, 0);
+    for (int b = 0; b < nb; ++b) surv_off[(size_t)b + 1] = surv_off[(size_t)b] + c->h_n_surv[b];
+    CTX_TRY(ensure_surv_capacity(c, surv_off[(size_t)nb]));
+    for (int b = 0; b < nb; ++b)
+        if (c->h_n_surv[b])
+            CTX_CUDA(cudaMemcpyAsync(c->h_surv + surv_off[(size_t)b], c->d_surv + (size_t)b * c->cand_cap,
+                                     sizeof(Surv) * c->h_n_surv[b], cudaMemcpyDeviceToHost, s));
+    if (c->prm.subpixel && (c->prm.flags & SIFT_GPU_FLAG_KEEP_UPSAMPLED))
+        for (int b = 0; b < nb; ++b)
+            if (imgs[(size_t)b].img->upsampled_out)
+                CTX_CUDA(cudaMemcpyAsync(imgs[(size_t)b].img->upsampled_out, c->d_up + (size_t)b * c->maxP[0],
+                                         sizeof(float) * level_px(p->ow[0], p->oh[0]), cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(cudaEventRecord(c->ev[5], s));
+    CTX_CUDA(cudaStreamSynchronize(s));
+
+    // host: order replay (one job per image)
+    const double t_host0 = now_ms();
+    std::vector<ReplayOut> rep((size_t)nb);
+    c->pool->parallel_for(nb, [&](int b) {
+        replay_image(c, p, c->h_n_cand[b], c->h_surv + surv_off[(size_t)b], c->h_n_surv[b], &rep[(size_t)b]);
+    });
+    size_t n_keys = 0;
+    for (int b = 0; b < nb; ++b) {
+        c->h_key_first[b] = (uint32_t)n_keys;
+        if (rep[(size_t)b].status == SIFT_GPU_OK) n_keys += rep[(size_t)b].keys.size();
+    }
+    c->h_key_first[nb] = (uint32_t)n_keys;
+    CTX_TRY(ensure_key_capacity(c, n_keys));
+    for (int b = 0; b < nb; ++b) {
+        if (rep[(size_t)b].status != SIFT_GPU_OK) continue;
+        const size_t off = c->h_key_first[b];
+        std::copy(rep[(size_t)b].keys.begin(), rep[(size_t)b].keys.end(), c->h_keys + off);
+        std::fill(c->h_key_img + off, c->h_key_img + off + rep[(size_t)b].keys.size(), (uint32_t)b);
+    }
+    c->tm.host_order_ms += (float)(now_ms() - t_host0);
+
+    CTX_CUDA(cudaEventRecord(c->ev[6], s));
+    float* h_desc = take_desc_block(c, n_keys * kDescLen);
+    if (!h_desc) return set_error(c, SIFT_GPU_E_CUDA, "pinned descriptor block allocation failed");
+    if (n_keys) {
+        CTX_CUDA(cudaMemcpyAsync(c->d_keys, c->h_keys, sizeof(KeyIn) * n_keys, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(c->d_key_img, c->h_key_img, sizeof(uint32_t) * n_keys, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(c->d_key_first, c->h_key_first, sizeof(uint32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, s));
+    }
+    CTX_CUDA(cudaEventRecord(c->ev[7], s));
+    const int n_targets = (int)p->targets_host.size();
+    if (n_keys) {
+        const size_t tables_need = (size_t)nb * (size_t)n_targets * 256;
+        if (tables_need > c->tables_cap) {
+            cudaFree(c->d_tables);
+            c->tables_cap = 0;
+            CTX_CUDA(cudaMalloc(&c->d_tables, sizeof(float) * tables_need));
+            c->tables_cap = tables_need;
+        }
+        CTX_TRY(launch_orientation(p->targets_dev, n_targets, c->d_keys, c->d_key_img, (uint32_t)n_keys, c->d_orient, c->d_npeaks,
+                                   c->d_peaks, s, L));
+    }
+    CTX_CUDA(cudaEventRecord(c->ev[8], s));
+    if (n_keys) {
+        CTX_TRY(launch_weight_tables(p->targets_dev, n_targets, c->d_taps + c->w16_blur.tap_off, c->w16_blur.r, c->d_tables, c->fma,
+                                     nb, s, L));
+        CTX_TRY(launch_descriptors(p->targets_dev, n_targets, c->d_tables, c->d_keys, c->d_key_img, c->d_key_first, (uint32_t)n_keys,
+                                   c->d_orient, c->d_desc, s, L));
+    }
+    CTX_CUDA(cudaEventRecord(c->ev[9], s));
+    if (n_keys) {
+        CTX_CUDA(cudaMemcpyAsync(c->h_orient, c->d_orient, sizeof(float) * n_keys, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(cudaMemcpyAsync(c->h_npeaks, c->d_npeaks, sizeof(uint32_t) * n_keys, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(cudaMemcpyAsync(h_desc, c->d_desc, sizeof(float) * kDescLen * n_keys, cudaMemcpyDeviceToHost, s));
+    }
+    CTX_CUDA(cudaEventRecord(c->ev[10], s));
+    CTX_CUDA(cudaStreamSynchronize(s));
+
+    // assemble results
+    for (int b = 0; b < nb; ++b) {
+        const int ri = imgs[(size_t)b].result_index;
+        sift_gpu_result& R = results[ri];
+        HostImageOut& HO = c->outs[(size_t)ri];
+        ReplayOut& ro = rep[(size_t)b];
+        R.n_candidates = c->h_n_cand[b];
+        R.n_survivors = ro.n_survivors;
+        R.out_width = p->ow[0]; R.out_height = p->oh[0];
+        R.status = ro.status;
+        R.n = 0; R.kps = nullptr; R.desc = nullptr;
+        if (ro.status != SIFT_GPU_OK) continue;
+        const size_t off = c->h_key_first[b];
+        // descriptors are contiguous per image only if every keypoint went to the device (always so in
+        // practice, sift.cpp:65 can never reject what sift.cpp:173 accepted); otherwise rows are spread out.
+        bool all = true;
+        for (size_t i = 0; i < ro.kps.size(); ++i) {
+            const uint32_t ko = ro.key_of[i];
+            if (ko == ~0u) { all = false; continue; }
+            if (c->h_npeaks[off + ko] > 1) R.status = SIFT_GPU_E_UNSUPPORTED;  // extra orientations (sift.cpp:194-200)
+            ro.kps[i].orientation = c->h_orient[off + ko];
+        }
+        HO.kps.swap(ro.kps);
+        R.n = (uint32_t)HO.kps.size();
+        R.kps = HO.kps.data();
+        if (all) {
+            R.desc = h_desc + off * kDescLen;
+        } else {
+            float* blk = take_desc_block(c, HO.kps.size() * kDescLen);
+            if (!blk) return set_error(c, SIFT_GPU_E_CUDA, "pinned descriptor block allocation failed");
+            for (size_t i = 0; i < HO.kps.size(); ++i) {
+                if (ro.key_of[i] == ~0u) std::memset(blk + i * kDescLen, 0, sizeof(float) * kDescLen);
+                else std::memcpy(blk + i * kDescLen, h_desc + (off + ro.key_of[i]) * kDescLen, sizeof(float) * kDescLen);
+            }
+            R.desc = blk;
+        }
+        if (R.status == SIFT_GPU_E_UNSUPPORTED)
+            c->error = "a keypoint produced more than one orientation peak (sift.cpp:194-200): not supported yet";
+    }
+    // stage times
+    float ms;
+    auto el = [&](int a, int b2) { cudaEventElapsedTime(&ms, c->ev[a], c->ev[b2]); return ms; };
+    c->tm.h2d_ms += el(0, 1);
+    c->tm.pyramid_ms += el(1, 2);
+    c->tm.extrema_ms += el(2, 3);
+    c->tm.eliminate_ms += el(3, 4);
+    c->tm.d2h_survivors_ms += el(4, 5);
+    c->tm.h2d_keypoints_ms += el(6, 7);
+    c->tm.orientation_ms += el(7, 8);
+    c->tm.descriptor_ms += el(8, 9);
+    c->tm.d2h_results_ms += el(9, 10);
+    return 0;
+}
+
+// =================================================================================================
+extern "C" {
+
+const char* sift_gpu_version(void) { return "sift_b200 0.1 (sm_100a)"; }
+
+const char* sift_gpu_last_error(const sift_gpu_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
+
+int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
+    if (!params || !out) return set_error(nullptr, SIFT_GPU_E_INVALID, "null argument");
+    *out = nullptr;
+    // reference asserts (sift.cpp:382-383)
+    if (!(params->octaves > 0)) return set_error(nullptr, SIFT_GPU_E_ASSERT, "assert(_octaves > 0)");
+    if (!(params->dogs_per_epoch >= 3)) return set_error(nullptr, SIFT_GPU_E_ASSERT, "assert(_dogsPerEpoch >= 3)");
+    if (params->octaves > kMaxOctaves || params->dogs_per_epoch + 1 > kMaxGauss)
+        return set_error(nullptr, SIFT_GPU_E_UNSUPPORTED, "too many octaves / DoGs per octave");
+    if (params->max_width < 1 || params->max_height < 1 || params->max_batch < 1)
+        return set_error(nullptr, SIFT_GPU_E_INVALID, "max_width/max_height/max_batch must be positive");
+    if ((params->subpixel ? 2 : 1) * (long)params->max_width > 65535 || (params->subpixel ? 2 : 1) * (long)params->max_height > 32767)
+        return set_error(nullptr, SIFT_GPU_E_UNSUPPORTED, "image too large for u16 keypoint coordinates");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= params->device || params->device < 0)
+        return set_error(nullptr, SIFT_GPU_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    sift_gpu_ctx* c = new sift_gpu_ctx();
+    c->prm = *params;
+    c->O = params->octaves; c->D = params->dogs_per_epoch; c->G = c->D + 1;
+    c->fma = (params->flags & SIFT_GPU_FLAG_FMA_BLUR) != 0;
+    c->B = params->max_batch;
+    c->max_in_w = params->max_width; c->max_in_h = params->max_height;
+    int rc = 0;
+    auto body = [&]() -> int {
+        CTX_CUDA(cudaSetDevice(params->device));
+        CTX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev) CTX_CUDA(cudaEventCreate(&e));
+        CTX_TRY(build_schedule(c));
+        CTX_TRY(alloc_buffers(c));
+        return 0;
+    };
+    rc = body();
+    if (rc != 0) {
+        std::string err = c->error;
+        sift_gpu_destroy(c);
+        g_last_error = err;
+        return rc;
+    }
+    int nthreads = 0;
+    if (const char* e = getenv("SIFT_GPU_HOST_THREADS")) nthreads = atoi(e);
+    if (nthreads <= 0) nthreads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    c->pool = new Pool(nthreads - 1);
+    *out = c;
+    return SIFT_GPU_OK;
+}
+
+void sift_gpu_destroy(sift_gpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    delete c->pool;
+    for (auto& kv : c->plans) {
+        Plan* p = kv.second;
+        cudaFree(p->d_maps); cudaFree(p->layers_dev); cudaFree(p->targets_dev);
+        delete p;
+    }
+    cudaFree(c->d_taps); cudaFree(c->d_in_u8); cudaFree(c->d_in); cudaFree(c->d_up_tmp); cudaFree(c->d_up); cudaFree(c->d_scratch);
+    for (int o = 0; o < kMaxOctaves; ++o)
+        for (int i = 0; i < kMaxGauss; ++i) { cudaFree(c->d_gauss[o][i]); cudaFree(c->d_dog[o][i]); }
+    cudaFree(c->d_mask); cudaFree(c->d_col_count); cudaFree(c->d_col_off); cudaFree(c->d_cands); cudaFree(c->d_surv);
+    cudaFree(c->d_n_cand); cudaFree(c->d_n_surv); cudaFreeHost(c->h_n_cand); cudaFreeHost(c->h_n_surv); cudaFreeHost(c->h_surv);
+    cudaFree(c->d_keys); cudaFree(c->d_key_img); cudaFree(c->d_key_first); cudaFree(c->d_orient); cudaFree(c->d_npeaks);
+    cudaFree(c->d_peaks); cudaFree(c->d_desc); cudaFree(c->d_tables);
+    cudaFreeHost(c->h_keys); cudaFreeHost(c->h_key_img); cudaFreeHost(c->h_key_first); cudaFreeHost(c->h_orient); cudaFreeHost(c->h_npeaks);
+    for (float* b : c->desc_blocks) cudaFreeHost(b);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, sift_gpu_result* results) {
+    if (!c || (n_images > 0 && (!images || !results)) || n_images < 0) return set_error(c, SIFT_GPU_E_INVALID, "null argument");
+    const double t0 = now_ms();
+    CTX_CUDA(cudaSetDevice(c->prm.device));
+    c->error.clear();
+    c->tm = sift_gpu_timings{};
+    c->desc_blocks_used = 0;
+    c->outs.clear();
+    c->outs.resize((size_t)n_images);
+    int first_error = SIFT_GPU_OK;
+    int i = 0;
+    while (i < n_images) {
+        const sift_gpu_image& im = images[i];
+        sift_gpu_result& R = results[i];
+        std::memset(&R, 0, sizeof R);
+        if (!im.data || im.width < 1 || im.height < 1 || (im.dtype != SIFT_GPU_DTYPE_F32 && im.dtype != SIFT_GPU_DTYPE_U8)) {
+            R.status = SIFT_GPU_E_INVALID;
+            if (!first_error) first_error = set_error(c, SIFT_GPU_E_INVALID, "bad image descriptor");
+            ++i;
+            continue;
+        }
+        if (im.width > c->max_in_w || im.height > c->max_in_h) {
+            R.status = SIFT_GPU_E_CAPACITY;
+            if (!first_error) first_error = set_error(c, SIFT_GPU_E_CAPACITY, "image larger than max_width x max_height");
+            ++i;
+            continue;
+        }
+        Plan* p = get_plan(c, im.width, im.height);
+        if (p->status != SIFT_GPU_OK) {
+            R.status = p->status;
+            if (!first_error) first_error = set_error(c, p->status, p->why);
+            ++i;
+            continue;
+        }
+        std::vector<ChunkImage> chunk;
+        while (i < n_images && (int)chunk.size() < c->B && images[i].data && images[i].width == im.width &&
+               images[i].height == im.height && images[i].dtype == im.dtype) {
+            std::memset(&results[i], 0, sizeof(sift_gpu_result));
+            chunk.push_back(ChunkImage{i, &images[i]});
+            ++i;
+        }
+        int rc = run_chunk(c, p, chunk, results);
+        if (rc != 0) return rc;
+        for (const ChunkImage& ci : chunk)
+            if (results[ci.result_index].status != SIFT_GPU_OK && !first_error) {
+                first_error = results[ci.result_index].status;
+                if (first_error == SIFT_GPU_E_PRECONDITION) c->error = "separableConvolveX(): kernel longer than line";
+            }
+    }
+    c->tm.device_total_ms = c->tm.h2d_ms + c->tm.pyramid_ms + c->tm.extrema_ms + c->tm.eliminate_ms + c->tm.d2h_survivors_ms +
+                            c->tm.h2d_keypoints_ms + c->tm.orientation_ms + c->tm.descriptor_ms + c->tm.d2h_results_ms;
+    c->tm.wall_ms = (float)(now_ms() - t0);
+    return first_error;
+}
+
+int sift_gpu_get_timings(const sift_gpu_ctx* c, sift_gpu_timings* out) {
+    if (!c || !out) return SIFT_GPU_E_INVALID;
+    *out = c->tm;
+    return SIFT_GPU_OK;
+}
+
+// ---- stage-level entry points -------------------------------------------------------------------
+int sift_gpu_debug_get_level(sift_gpu_ctx* c, int image_idx, int octave, int elem, int kind, float* out, int* width,
+                             int* height, float* scale) {
+    if (!c || !c->last_plan) return set_error(c, SIFT_GPU_E_INVALID, "no pass has run yet");
+    const Plan* p = c->last_plan;
+    if (image_idx < 0 || image_idx >= c->last_batch || octave < 0 || octave >= c->O || elem < 0 ||
+        elem >= (kind == SIFT_GPU_KIND_DOG ? c->D : c->G))
+        return set_error(c, SIFT_GPU_E_INVALID, "level index out of range");
+    CTX_CUDA(cudaSetDevice(c->prm.device));
+    const float* src = (kind == SIFT_GPU_KIND_DOG ? c->d_dog[octave][elem] : c->d_gauss[octave][elem]) + (size_t)image_idx * c->maxP[octave];
+    if (width) *width = p->ow[octave];
+    if (height) *height = p->oh[octave];
+    if (scale) *scale = kind == SIFT_GPU_KIND_DOG ? c->d_scale[octave][elem] : c->g_scale[octave][elem];
+    if (out) CTX_CUDA(cudaMemcpy(out, src, sizeof(float) * level_px(p->ow[octave], p->oh[octave]), cudaMemcpyDeviceToHost));
+    return SIFT_GPU_OK;
+}
+
+static int upload(sift_gpu_ctx* c, const float* h, size_t n, float** d) {
+    CTX_CUDA(cudaMalloc(d, sizeof(float) * n));
+    CTX_CUDA(cudaMemcpy(*d, h, sizeof(float) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, float sigma, float* dst, int mode) {
+    if (!c || !src || !dst || w < 1 || h < 1) return set_error(c, SIFT_GPU_E_INVALID, "bad argument");
+    CTX_CUDA(cudaSetDevice(c->prm.device));
+    int r = 0;
+    std::vector<float> taps = gaussian_taps(sigma, &r);
+    if (w < r + 1 || h < r + 1) return set_error(c, SIFT_GPU_E_PRECONDITION, "separableConvolveX/Y(): kernel longer than line");
+    if (r > kMaxTileRadius) return set_error(c, SIFT_GPU_E_UNSUPPORTED, "radius too large");
+    int dw = w, dh = h;
+    if (mode == 1) { dw = (w + 1) / 2; dh = (h + 1) / 2; }
+    if (mode == 2) { dw = 2 * w; dh = 2 * h; }
+    if (mode != 0 && !(w > 1 && h > 1 && dw > 1 && dh > 1)) return set_error(c, SIFT_GPU_E_PRECONDITION, "resizeImageNoInterpolation(): image too small");
+    float *d_src = nullptr, *d_dst = nullptr, *d_taps = nullptr, *d_out = nullptr;
+    int* d_map = nullptr;
+    const size_t n = level_px(w, h);
+    int rc = upload(c, src, n, &d_src);
+    if (!rc) rc = upload(c, taps.data(), taps.size(), &d_taps);
+    if (!rc && cudaMalloc(&d_dst, sizeof(float) * n) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    if (!rc) {
+        BlurArgs a{};
+        a.src = d_src; a.dst = d_dst; a.w = w; a.h = h; a.taps = d_taps; a.r = r;
+        rc = launch_blur(a, 1, c->fma, c->stream, nullptr);
+    }
+    const float* result = d_dst;
+    if (!rc && mode != 0) {
+        std::vector<int> mx = resize_index_map(w, dw), my = resize_index_map(h, dh);
+        std::vector<int> both(mx);
+        both.insert(both.end(), my.begin(), my.end());
+        if (cudaMalloc(&d_map, sizeof(int) * both.size()) != cudaSuccess || cudaMalloc(&d_out, sizeof(float) * level_px(dw, dh)) != cudaSuccess ||
+            cudaMemcpy(d_map, both.data(), sizeof(int) * both.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = SIFT_GPU_E_CUDA;
+        if (!rc) rc = launch_resize_nn(d_dst, 0, w, h, d_out, 0, dw, dh, d_map, d_map + dw, 1, c->stream, nullptr);
+        result = d_out;
+    }
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    if (!rc && cudaMemcpy(dst, result, sizeof(float) * level_px(dw, dh), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_taps); cudaFree(d_out); cudaFree(d_map);
+    if (rc == SIFT_GPU_E_CUDA && c->error.empty()) c->error = "CUDA failure in debug blur";
+    return rc;
+}
+
+int sift_gpu_debug_blur(sift_gpu_ctx* c, const float* src, int w, int h, float sigma, float* dst) { return debug_blur_impl(c, src, w, h, sigma, dst, 0); }
+int sift_gpu_debug_reduce(sift_gpu_ctx* c, const float* src, int w, int h, float sigma, float* dst) { return debug_blur_impl(c, src, w, h, sigma, dst, 1); }
+int sift_gpu_debug_increase(sift_gpu_ctx* c, const float* src, int w, int h, float sigma, float* dst) { return debug_blur_impl(c, src, w, h, sigma, dst, 2); }
+
+struct DebugLayers {
+    float* d[3] = {nullptr, nullptr, nullptr};
+    ScanLayer L{};
+    ScanLayer* dev = nullptr;
+    uint32_t *mask = nullptr, *cc = nullptr, *co = nullptr, *n_cand = nullptr;
+    Cand* cands = nullptr;
+    ~DebugLayers() {
+        for (float* p : d) cudaFree(p);
+        cudaFree(dev); cudaFree(mask); cudaFree(cc); cudaFree(co); cudaFree(n_cand); cudaFree(cands);
+    }
+};
+
+static int debug_layers_setup(sift_gpu_ctx* c, DebugLayers& S, const float* d0, const float* d1, const float* d2, int w, int h) {
+    const float* hs[3] = {d0, d1, d2};
+    const size_t n = level_px(w, h);
+    for (int i = 0; i < 3; ++i) CTX_TRY(upload(c, hs[i], n, &S.d[i]));
+    S.L.d0 = S.d[0]; S.L.d1 = S.d[1]; S.L.d2 = S.d[2];
+    S.L.stride = 0; S.L.w = w; S.L.h = h; S.L.n_yw = (h + 31) / 32; S.L.mask_off = 0; S.L.col_base = 0; S.L.octave = 0; S.L.index = 1;
+    CTX_CUDA(cudaMalloc(&S.dev, sizeof(ScanLayer)));
+    CTX_CUDA(cudaMemcpy(S.dev, &S.L, sizeof(ScanLayer), cudaMemcpyHostToDevice));
+    CTX_CUDA(cudaMalloc(&S.mask, sizeof(uint32_t) * (size_t)S.L.n_yw * (size_t)w));
+    CTX_CUDA(cudaMalloc(&S.cc, sizeof(uint32_t) * (size_t)w));
+    CTX_CUDA(cudaMalloc(&S.co, sizeof(uint32_t) * (size_t)w));
+    CTX_CUDA(cudaMalloc(&S.n_cand, sizeof(uint32_t)));
+    CTX_CUDA(cudaMalloc(&S.cands, sizeof(Cand) * n));
+    return 0;
+}
+
+int sift_gpu_debug_extrema(sift_gpu_ctx* c, const float* d0, const float* d1, const float* d2, int w, int h, uint16_t* xs,
+                           uint16_t* ys, uint32_t capacity, uint32_t* n_out) {
+    if (!c || !d0 || !d1 || !d2 || w < 1 || h < 1 || !n_out) return set_error(c, SIFT_GPU_E_INVALID, "bad argument");
+    CTX_CUDA(cudaSetDevice(c->prm.device));
+    DebugLayers S;
+    CTX_TRY(debug_layers_setup(c, S, d0, d1, d2, w, h));
+    CTX_TRY(launch_extrema(S.dev, &S.L, 1, w, (uint32_t)S.L.n_yw * (uint32_t)w, S.mask, S.cc, S.co, S.cands, 0, S.n_cand, 1, c->stream, nullptr));
+    CTX_CUDA(cudaStreamSynchronize(c->stream));
+    uint32_t n = 0;
+    CTX_CUDA(cudaMemcpy(&n, S.n_cand, sizeof n, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    std::vector<Cand> hc(n);
+    if (n) CTX_CUDA(cudaMemcpy(hc.data(), S.cands, sizeof(Cand) * n, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n && i < capacity; ++i) { xs[i] = hc[i].x; ys[i] = hc[i].y; }
+    return SIFT_GPU_OK;
+}
+
+int sift_gpu_debug_eliminate(sift_gpu_ctx* c, const float* d0, const float* d1, const float* d2, int w, int h,
+                             const uint16_t* xs, const uint16_t* ys, uint32_t n, uint8_t* filtered) {
+    if (!c || !d0 || !d1 || !d2 || w < 3 || h < 3 || (n && (!xs || !ys || !filtered))) return set_error(c, SIFT_GPU_E_INVALID, "bad argument");
+    CTX_CUDA(cudaSetDevice(c->prm.device));
+    DebugLayers S;
+    CTX_TRY(debug_layers_setup(c, S, d0, d1, d2, w, h));
+    std::vector<Cand> hc(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (xs[i] < 1 || xs[i] > w - 2 || ys[i] < 1 || ys[i] > h - 2) return set_error(c, SIFT_GPU_E_INVALID, "candidate on the border");
+        hc[i] = Cand{xs[i], ys[i], 0, 1, 0, 0};
+    }
+    Cand* d_c = nullptr; Surv* d_s = nullptr; uint32_t* d_ns = nullptr;
+    int rc = 0;
+    if (cudaMalloc(&d_c, sizeof(Cand) * std::max<uint32_t>(n, 1)) != cudaSuccess || cudaMalloc(&d_s, sizeof(Surv) * std::max<uint32_t>(n, 1)) != cudaSuccess ||
+        cudaMalloc(&d_ns, sizeof(uint32_t)) != cudaSuccess)
+        rc = SIFT_GPU_E_CUDA;
+    if (!rc && n && cudaMemcpy(d_c, hc.data(), sizeof(Cand) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    if (!rc && cudaMemcpy(S.n_cand, &n, sizeof n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    if (!rc) rc = launch_eliminate(S.dev, 1, d_c, 0, S.n_cand, d_s, std::max<uint32_t>(n, 1), d_ns, 3, 1, c->stream, nullptr);
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    if (!rc && n && cudaMemcpy(hc.data(), d_c, sizeof(Cand) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    cudaFree(d_c); cudaFree(d_s); cudaFree(d_ns);
+    if (rc) return set_error(c, rc, "CUDA failure in debug eliminate");
+    for (uint32_t i = 0; i < n; ++i) filtered[i] = hc[i].filtered;
+    return SIFT_GPU_OK;
+}
+
+int sift_gpu_debug_get_candidates(sift_gpu_ctx* c, int image_idx, uint16_t* xs, uint16_t* ys, uint16_t* octave, uint16_t* index,
+                                  uint8_t* filtered, uint32_t capacity, uint32_t* n_out) {
+    if (!c || !c->last_plan || image_idx < 0 || image_idx >= c->last_batch || !n_out) return set_error(c, SIFT_GPU_E_INVALID, "bad argument");
+    CTX_CUDA(cudaSetDevice(c->prm.device));
+    uint32_t n = 0;
+    CTX_CUDA(cudaMemcpy(&n, c->d_n_cand + image_idx, sizeof n, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    const uint32_t m = std::min(n, capacity);
+    std::vector<Cand> hc(m);
+    if (m) CTX_CUDA(cudaMemcpy(hc.data(), c->d_cands + (size_t)image_idx * c->cand_cap, sizeof(Cand) * m, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < m; ++i) {
+        if (xs) xs[i] = hc[i].x;
+        if (ys) ys[i] = hc[i].y;
+        if (octave) octave[i] = hc[i].octave;
+        if (index) index[i] = hc[i].index;
+        if (filtered) filtered[i] = hc[i].filtered;
+    }
+    return SIFT_GPU_OK;
+}
+
+int sift_gpu_debug_sort_order(const uint8_t* filtered, uint32_t n, uint32_t* order) {
+    if ((n && (!filtered || !order))) return SIFT_GPU_E_INVALID;
+    std::vector<uint32_t> v(n);
+    for (uint32_t i = 0; i < n; ++i) v[i] = i | (filtered[i] ? 0x80000000u : 0u);
+    std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
+    for (uint32_t i = 0; i < n; ++i) order[i] = v[i] & 0x7fffffffu;
+    return SIFT_GPU_OK;
+}
+
+}  // extern "C"
