@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: 1080p images/s through the CUDA SIFT pipeline (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one pass of the whole path (pyramid -> extrema -> elimination -> order replay -> orientation
+-> descriptors) over one batch of synthetic 1920x1080 frames (5 octaves, 3 DoGs/octave, sigma 1.6,
+k sqrt(2), no upsample: BASELINE.json configs[2]/[4]) per GPU.  `value` is measured with the frames
+already resident in HBM; `e2e` goes through the same C-ABI call with pinned HOST buffers, so every
+step pays the host->device copy of its frames and the device->host copy of keypoints + descriptors.
+One process per GPU (torchrun for N > 1); images are independent, so ranks share nothing on the data
+path (weak scaling) and torch.distributed only provides the barrier and the max-over-ranks reduction.
+
+--impl reference times the CPU restatement of the reference's own algorithm (oracle/, the reference
+itself cannot be built here: Vigra/OpenCV/Boost are absent) on all host cores, same metric and config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, OCTAVES, DPE = 1920, 1080, 5, 3
+WORKLOAD = "1920x1080 synthetic frames (blobs+corners+-2 noise, seed=frame index), 5 octaves, 3 DoGs/octave, sigma 1.6, k sqrt(2), subpixel 0"
+
+
+def pyramid_bytes(w, h, octaves, dpe, subpixel):
+    """Algorithmic bytes of the pyramid + DoG stage, SURVEY.md §8(d): every image read/written once where
+    semantically required, fp32."""
+    in_px = w * h
+    if subpixel:
+        w, h = 2 * w, 2 * h
+    px = []
+    for _ in range(octaves):
+        px.append(w * h)
+        w, h = (w + 1) // 2, (h + 1) // 2
+    a = 4 * (in_px + in_px) + 4 * (in_px + px[0]) if subpixel else 4 * (px[0] + px[0])
+    b = sum(4 * p * (3 * dpe - 1) for p in px)
+    c = sum(4 * (px[o] + px[o + 1]) for o in range(octaves - 1))
+    return a + b + c
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle's restatement of the reference path (hoisted flavour: identical results, without the
+    reference's per-candidate image copies and per-keypoint full-image blur) on all host cores."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from sift_b200.synth import synth_frame
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = [synth_frame(W, H, i) for i in range(min(cores, 16))]
+    k = float(np.float32(np.sqrt(2.0)))
+    oracles = [ol.Oracle(DPE, OCTAVES, 1.6, k, False) for _ in range(cores)]
+
+    def step():
+        def job(t):
+            oracles[t].calculate(frames[t % len(frames)])
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(job, range(cores)))
+        return cores
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        n += step()
+    dt = time.perf_counter() - t0
+    v = n / dt
+    line = {"impl": "reference", "metric": "1080p images/sec end-to-end SIFT", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": cores},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{cores} 1080p frames per step, one per host thread, oracle 'hoisted' flavour"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(seconds_budget=12.0):
+    """Single-thread CPU baseline next to the GPU number: the oracle (kind 'port') on 1080p frames, bounded."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from sift_b200.synth import synth_frame
+
+    o = ol.Oracle(DPE, OCTAVES, 1.6, float(np.float32(np.sqrt(2.0))), False)
+    n, t = 0, 0.0
+    while t < seconds_budget and n < 16:
+        dt, _ = o.time_calculate(synth_frame(W, H, n))
+        t += dt
+        n += 1
+    return {"value": n / t, "unit": "images/s", "cores": 1, "kind": "port",
+            "sample": f"{n} synthetic 1080p frames, oracle 'hoisted' flavour (reference results without its O(pixels^2) copies), 1 thread"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from sift_b200 import capi, shard
+    from sift_b200.synth import synth_frame
+
+    rank, local_rank, world = shard.world()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = shard.init_process_group("nccl") if world > 1 else None
+
+    B, n_distinct = args.batch, args.frames
+    # weak scaling: every rank owns its own range of the global frame sequence
+    lo, _ = shard.shard_range(n_distinct * world, rank, world)
+    host_frames = torch.empty((n_distinct, H, W), dtype=torch.float32).pin_memory()
+    for i in range(n_distinct):
+        host_frames[i] = torch.from_numpy(synth_frame(W, H, lo + i))
+    dev_frames = host_frames.to(dev)  # 64 x 8.3 MB = 531 MB > L2 (126 MB): successive steps cannot be served from L2
+    torch.cuda.synchronize()
+
+    g = capi.SiftGpu(DPE, OCTAVES, 1.6, capi.SQRT2_F32, False, max_width=W, max_height=H, max_batch=args.device_batch,
+                     device=local_rank, flags=args.flags)
+
+    def descs(base_ptr, memory, step):
+        arr = (capi.Image * B)()
+        for j in range(B):
+            f = (step * B + j) % n_distinct
+            arr[j] = capi.Image(base_ptr + f * W * H * 4, W, H, 0, capi.DTYPE_F32, memory, None)
+        return arr
+
+    def do_steps(base_ptr, memory, n_steps, first):
+        acc = {"pyramid_ms": 0.0, "span_ms": 0.0, "launches": 0, "kps": 0, "cands": 0, "surv": 0, "device_total_ms": 0.0,
+               "host_order_ms": 0.0, "stages": {}}
+        for s in range(n_steps):
+            rc, res = g.run_raw(descs(base_ptr, memory, first + s), B)
+            if rc != 0:
+                raise g._err(rc)
+            t = g.timings()
+            acc["pyramid_ms"] += t["pyramid_ms"]; acc["span_ms"] += t["span_ms"]; acc["launches"] += int(t["kernel_launches"])
+            acc["device_total_ms"] += t["device_total_ms"]; acc["host_order_ms"] += t["host_order_ms"]
+            for k2, v in t.items():
+                if k2.endswith("_ms"):
+                    acc["stages"][k2] = acc["stages"].get(k2, 0.0) + v
+            for r in res:
+                acc["kps"] += r.n; acc["cands"] += r.n_candidates; acc["surv"] += r.n_survivors
+        return acc
+
+    def timed(base_ptr, memory):
+        do_steps(base_ptr, memory, args.warmup, 0)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        acc = do_steps(base_ptr, memory, args.steps, args.warmup)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if dist:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        return wall, acc, clocks
+
+    wall_d, acc_d, clocks = timed(dev_frames.data_ptr(), capi.MEM_DEVICE)
+    wall_h, acc_h, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
+
+    # run() is synchronous (it returns after its last stream sync), so the host clock around the K steps equals the
+    # device-side span; span_ms (CUDA events on the library's stream) is reported beside it.  Max over ranks.
+    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_d["pyramid_ms"]],
+                                    [args.steps * B, acc_d["launches"], acc_d["kps"], acc_d["cands"]])
+    if rank != 0:
+        g.close()
+        return
+    wall_d, wall_h, span_d, pyr_ms = mx
+    images, launches, kps, cands = sm
+    value = images / wall_d
+    e2e = images / wall_h
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    pyr_bytes = pyramid_bytes(W, H, OCTAVES, DPE, False)
+    achieved = pyr_bytes * args.steps * B / (pyr_ms * 1e-3) / 1e9  # per rank: bytes of this rank's frames / its pyramid time
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "pyramid_traffic.json"))).get("dram_bytes_per_image")
+    except Exception:
+        pass
+    per_img_h2d = W * H * 4
+    d2h = (acc_h["kps"] * (20 + 512) + acc_h["surv"] * 12) / max(1, args.steps) + 8 * B
+    line = {
+        "metric": "1080p images/sec end-to-end SIFT", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall_d / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "distinct_frames_per_gpu": n_distinct, "device_batch": args.device_batch,
+                   "l2": "inputs larger than L2 (distinct frames cycled: %d MB per GPU)" % (n_distinct * per_img_h2d // 1000000),
+                   "order": "canonical" if args.flags & capi.FLAG_ORDER_CANONICAL else "reference std::sort replay",
+                   "blur": "fma" if args.flags & capi.FLAG_FMA_BLUR else "exact mul+add (bit-identical to the oracle)",
+                   "keypoints_per_image": kps / images, "candidates_per_image": cands / images},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * per_img_h2d, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * wall_h / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "pyramid+DoG stage (blur/DoG/decimation launches of one device pass)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "algorithmic_bytes_per_image": pyr_bytes, "pyramid_ms_per_image": pyr_ms / (args.steps * B), "traffic": traffic},
+        "device_span_ms_per_step": span_d / args.steps,
+        "stage_ms_per_image": {k2: v / (args.steps * B) for k2, v in acc_d["stages"].items()},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    else:
+        line["cpu_baseline"] = None
+    g.close()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=64, help="distinct synthetic frames per GPU (cycled)")
+    ap.add_argument("--device-batch", type=int, default=32, help="frames per device pass (ctx max_batch)")
+    ap.add_argument("--flags", type=int, default=0, help="SIFT_GPU_FLAG_* bits (1 canonical order, 4 FMA blur)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

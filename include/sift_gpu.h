@@ -98,7 +98,9 @@ typedef struct sift_gpu_timings {
     float host_order_ms;
     float h2d_keypoints_ms, orientation_ms, descriptor_ms, d2h_results_ms;
     float device_total_ms; /* sum of device stages */
-    float wall_ms;         /* whole run() */
+    float wall_ms;         /* whole run(), host clock */
+    float span_ms;         /* CUDA-event time from the first enqueue to the last completion of every device pass
+                              (includes the host order replay that sits between the two device halves) */
     uint64_t kernel_launches;
 } sift_gpu_timings;
 

@@ -48,7 +48,7 @@ class Result(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "pyramid_ms", "extrema_ms", "eliminate_ms", "d2h_survivors_ms",
                                          "host_order_ms", "h2d_keypoints_ms", "orientation_ms", "descriptor_ms",
-                                         "d2h_results_ms", "device_total_ms", "wall_ms")] + [("kernel_launches", C.c_uint64)]
+                                         "d2h_results_ms", "device_total_ms", "wall_ms", "span_ms")] + [("kernel_launches", C.c_uint64)]
 
 
 class SiftGpuError(RuntimeError):

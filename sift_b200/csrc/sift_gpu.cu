@@ -783,6 +783,7 @@ static int run_chunk(sift_gpu_ctx* c, Plan* p, const std::vector<ChunkImage>& im
     c->tm.orientation_ms += el(7, 8);
     c->tm.descriptor_ms += el(8, 9);
     c->tm.d2h_results_ms += el(9, 10);
+    c->tm.span_ms += el(0, 10);
     return 0;
 }
 
