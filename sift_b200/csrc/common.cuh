@@ -1,5 +1,6 @@
 // Shared declarations of the sm_100a kernels behind include/sift_gpu.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -7,9 +8,9 @@ namespace siftgpu {
 
 constexpr int kMaxOctaves = 12;
 constexpr int kMaxGauss = 12;   // dogs_per_epoch + 1
-constexpr int kMaxRadius = 255; // taps per blur = 2r+1 <= 511
 constexpr int kDescLen = 128;
 constexpr int kRegion = 8;      // reference sift.cpp:61,164
+constexpr int kPitchAlign = 32; // row pitch of every device image is a multiple of 32 floats (128 B): TMA needs 16-B strides
 
 // One emitted extremum (reference sift.cpp:373), canonical (octave, index, x, y) order.
 struct Cand {
@@ -36,10 +37,11 @@ struct KeyIn {
 };
 static_assert(sizeof(KeyIn) == 8, "KeyIn");
 
-// A pyramid level as the kernels see it: image b lives at base + b*stride.
+// A pyramid level as the kernels see it: pixel (x, y) of image b lives at base[b*stride + y*pitch + x].
 struct LevelRef {
     float* base;
     size_t stride; // elements between consecutive images of the batch
+    int pitch;     // elements between consecutive rows
     int w, h;
 };
 
@@ -49,6 +51,7 @@ struct ScanLayer {
     const float* d1;
     const float* d2;
     size_t stride;       // elements between images
+    int pitch;
     int w, h;
     int n_yw;            // ceil(h/32) mask words per column
     uint32_t mask_off;   // word offset of this layer inside one image's mask block
@@ -56,14 +59,21 @@ struct ScanLayer {
     uint8_t octave, index;
 };
 
+// One Gaussian blur launch: dst = blur(src); optional dog = 128 + (dst - src); optional decimation
+// (alg::reduceToNextLevel fused: only the pixels the nearest-neighbour resize picks are stored).
 struct BlurArgs {
     const float* src;
-    float* dst;      // blurred image (may be null when only the DoG is wanted)
-    float* dog;      // 128 + (dst - src), or null
+    float* dst;      // may be null when only the DoG is wanted
+    float* dog;      // or null
     size_t src_stride, dst_stride, dog_stride; // per-image strides (elements)
+    int src_pitch, dst_pitch, dog_pitch;
     int w, h;
-    const float* taps; // 2r+1 taps, device memory
+    const float* taps;      // 2r+1 taps, device memory
+    const float* taps_host; // same taps, host memory (kernel-parameter copy for the streaming kernel)
     int r;
+    const int* sel_x; // decimation: destination column of source column x, or -1 (device); null = no decimation
+    const int* sel_y;
+    const CUtensorMap* map; // host pointer to the TMA descriptor of src (box = stream_box_width(r)), or null
 };
 
 #define SIFT_CUDA_TRY(expr)                                         \
@@ -76,10 +86,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // ---- launchers (each returns 0 or SIFT_GPU_E_CUDA; they count their launches in *launches) ----
 int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t* launches);
-int launch_resize_nn(const float* src, size_t src_stride, int sw, int sh, float* dst, size_t dst_stride, int dw, int dh,
-                     const int* map_x, const int* map_y, int batch, cudaStream_t s, uint64_t* launches);
-int launch_u8_to_f32(const uint8_t* src, size_t src_stride, float* dst, size_t dst_stride, size_t n, int batch,
-                     cudaStream_t s, uint64_t* launches);
+int stream_box_width(int r);   // TMA box width the streaming kernel needs for radius r, or 0 if r has no streaming kernel
+int max_generic_radius();      // largest radius the generic tile kernel can hold in shared memory
+int launch_resize_nn(const float* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int dw,
+                     int dh, const int* map_x, const int* map_y, int batch, cudaStream_t s, uint64_t* launches);
+int launch_u8_to_f32(const uint8_t* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int w,
+                     int h, int batch, cudaStream_t s, uint64_t* launches);
 
 int launch_extrema(const ScanLayer* layers_dev, const ScanLayer* layers_host, int n_layers, int total_cols,
                    uint32_t mask_words_per_image, uint32_t* mask, uint32_t* col_count, uint32_t* col_off,

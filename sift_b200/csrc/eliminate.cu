@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) eliminate_kernel(const ScanLayer* __restr
             const float* D0 = L.d0 + off;
             const float* D1 = L.d1 + off;
             const float* D2 = L.d2 + off;
-            const int w = L.w, x = c.x, y = c.y;
+            const int w = L.pitch, x = c.x, y = c.y;
 #define AT(D, xx, yy) D[(size_t)(yy) * w + (xx)]
             // algorithms.cpp:69-71
             const float dx = (AT(D1, x - 1, y) - AT(D1, x + 1, y)) / 2;

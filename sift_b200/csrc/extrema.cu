@@ -29,8 +29,8 @@ __global__ void __launch_bounds__(kExThreads) extrema_mask_kernel(ScanLayer L, u
             const int yp = ybeg - 1 < 0 ? 0 : ybeg - 1;
 #pragma unroll
             for (int l = 0; l < 3; ++l) {
-                pl[l] = d[l][(size_t)yp * L.w + x - 1];
-                pc[l] = d[l][(size_t)yp * L.w + x];
+                pl[l] = d[l][(size_t)yp * L.pitch + x - 1];
+                pc[l] = d[l][(size_t)yp * L.pitch + x];
             }
         }
 #pragma unroll 4
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(kExThreads) extrema_mask_kernel(ScanLayer L, u
             float cl[3], cc[3];
 #pragma unroll
             for (int l = 0; l < 3; ++l) {
-                cl[l] = d[l][(size_t)y * L.w + x - 1];
-                cc[l] = d[l][(size_t)y * L.w + x];
+                cl[l] = d[l][(size_t)y * L.pitch + x - 1];
+                cc[l] = d[l][(size_t)y * L.pitch + x];
             }
             const float v = cc[0];
             bool gt = false, lt = false;

@@ -21,15 +21,15 @@ constexpr int kWin = 2 * kRegion;  // 16
 
 // alg::gradientMagnitude / gradientOrientation at interior pixel (x, y); 0 on the 1-px border
 // (the pyramids are zero-initialised and only the interior is filled, sift.cpp:137-138).
-__device__ __forceinline__ void gradient_at(const float* __restrict__ G, int w, int h, int x, int y, float* mag,
+__device__ __forceinline__ void gradient_at(const float* __restrict__ G, int pitch, int w, int h, int x, int y, float* mag,
                                             float* ori) {
     if (x < 1 || y < 1 || x > w - 2 || y > h - 2) {
         *mag = 0.0f;
         *ori = 0.0f;
         return;
     }
-    const float dx = G[(size_t)y * w + x + 1] - G[(size_t)y * w + x - 1];
-    const float dy = G[(size_t)(y + 1) * w + x] - G[(size_t)(y - 1) * w + x];
+    const float dx = G[(size_t)y * pitch + x + 1] - G[(size_t)y * pitch + x - 1];
+    const float dy = G[(size_t)(y + 1) * pitch + x] - G[(size_t)(y - 1) * pitch + x];
     *mag = (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
     const float r = atan2f(dy, dx);
     const float s = r + 360.0f;
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(128) orientation_kernel(const LevelRef* __rest
         for (int s = lane; s < kWin * kWin; s += 32) {
             const int wx = s >> 4, wy = s & 15;
             float mag, ori;
-            gradient_at(G, T.w, T.h, x0 + wx, y0 + wy, &mag, &ori);
-            const float g = G[(size_t)(y0 + wy) * T.w + x0 + wx];
+            gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &mag, &ori);
+            const float g = G[(size_t)(y0 + wy) * T.pitch + x0 + wx];
             s_val[wib][s] = mag * g;
             uint16_t bi = (uint16_t)(int)floorf(ori / 10);
             s_bin[wib][s] = bi % 35;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) weight_table_kernel(const LevelRef* __res
         float sum = 0.0f;
         if (x < T.w)
             for (int j = 0; j <= 2 * r; ++j) {
-                const float v = G[(size_t)y * T.w + refl(x + j - r, T.w)];
+                const float v = G[(size_t)y * T.pitch + refl(x + j - r, T.w)];
                 sum = FMA ? fmaf(taps[2 * r - j], v, sum) : __fadd_rn(sum, __fmul_rn(taps[2 * r - j], v));
             }
         s_tmp[i] = sum;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int s = lane + 32 * j, wx = s >> 4, wy = s & 15;
-            gradient_at(G, T.w, T.h, x0 + wx, y0 + wy, &M[j], &O[j]);
+            gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &M[j], &O[j]);
         }
         // replay earlier keypoints of this image and level whose window overlaps, in vector order
         const uint32_t first = key_first[img];
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
             const int s = lane + 32 * j, wx = s >> 4, wy = s & 15;
             O[j] = O[j] + theta;
             M[j] = M[j] + W[wy * kWin + wx];
-            const float g = G[(size_t)(y0 + wy) * T.w + x0 + wx];
+            const float g = G[(size_t)(y0 + wy) * T.pitch + x0 + wx];
             s_val[wib][s] = M[j] * g;
             uint16_t bi = (uint16_t)(int)floorf(O[j] / 45);
             s_bin[wib][s] = bi % 7;

@@ -22,6 +22,7 @@
 
 #include "../../include/sift_gpu.h"
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace siftgpu {
 
@@ -134,14 +135,19 @@ struct BlurSpec {
     size_t tap_off = 0;  // offset into the device tap pool
 };
 
+static int pitch_of(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
+
 struct Plan {
-    int in_w = 0, in_h = 0;
-    int ow[kMaxOctaves] = {0}, oh[kMaxOctaves] = {0};
+    int in_w = 0, in_h = 0, in_pitch = 0;
+    int ow[kMaxOctaves] = {0}, oh[kMaxOctaves] = {0}, pitch[kMaxOctaves] = {0};
+    // TMA descriptors of the blur sources (valid[] says whether the streaming kernel can be used)
+    CUtensorMap map_up, map_base, map_chain[kMaxOctaves][kMaxGauss], map_reduce[kMaxOctaves];
+    bool has_up = false, has_base = false, has_chain[kMaxOctaves][kMaxGauss] = {{false}}, has_reduce[kMaxOctaves] = {false};
+    size_t sel_x[kMaxOctaves] = {0}, sel_y[kMaxOctaves] = {0};  // decimation: inverse index maps (offsets into d_maps)
     int status = SIFT_GPU_OK;
     std::string why;
     int* d_maps = nullptr;  // all index maps, one allocation
     size_t up_mx = 0, up_my = 0;
-    size_t red_mx[kMaxOctaves] = {0}, red_my[kMaxOctaves] = {0};
     std::vector<ScanLayer> layers_host;
     ScanLayer* layers_dev = nullptr;
     int total_cols = 0;
@@ -175,12 +181,13 @@ struct sift_gpu_ctx {
     BlurSpec chain_blur[kMaxOctaves][kMaxGauss];
     BlurSpec reduce_blur[kMaxOctaves];
     float* d_taps = nullptr;
+    std::vector<float> h_taps;
     int dead_blur_r[kMaxOctaves][kMaxGauss]{};
 
     // sizing
     int B = 1;
-    int max_in_w = 0, max_in_h = 0;
-    size_t max_in_px = 0;
+    int max_in_w = 0, max_in_h = 0, max_in_pitch = 0;
+    size_t max_in_px = 0;       // per-image stride of the input staging buffers (pitched)
     size_t maxP[kMaxOctaves]{};
     size_t cand_cap = 0;
 
@@ -189,7 +196,6 @@ struct sift_gpu_ctx {
     float* d_in = nullptr;
     float* d_up_tmp = nullptr;  // blur(img, 1.0) at input resolution
     float* d_up = nullptr;      // 2x image
-    float* d_scratch = nullptr; // full-resolution blur before decimation
     float* d_gauss[kMaxOctaves][kMaxGauss]{};
     float* d_dog[kMaxOctaves][kMaxGauss]{};
     uint32_t* d_mask = nullptr;
@@ -287,6 +293,7 @@ static int build_schedule(sift_gpu_ctx* c) {
             (void)gaussian_taps((float)(1.5 * (double)c->d_scale[e][i]), &r);  // sift.cpp:184
             c->dead_blur_r[e][i] = r;
         }
+    c->h_taps = pool;
     CTX_CUDA(cudaMalloc(&c->d_taps, sizeof(float) * pool.size()));
     CTX_CUDA(cudaMemcpy(c->d_taps, pool.data(), sizeof(float) * pool.size(), cudaMemcpyHostToDevice));
     return 0;
@@ -312,22 +319,21 @@ static void nearest_gaussian(const sift_gpu_ctx* c, float scale, int* o_out, int
     *o_out = bo; *i_out = bi;
 }
 
-static constexpr int kMaxTileRadius = 80;  // what the generic tile kernel's shared memory holds
-
 static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
     auto key = std::make_pair(in_w, in_h);
     auto it = c->plans.find(key);
     if (it != c->plans.end()) return it->second;
     Plan* p = new Plan();
     c->plans[key] = p;
-    p->in_w = in_w; p->in_h = in_h;
+    p->in_w = in_w; p->in_h = in_h; p->in_pitch = pitch_of(in_w);
     octave_dims(c, in_w, in_h, p->ow, p->oh);
     const int O = c->O, D = c->D;
+    for (int o = 0; o < O; ++o) p->pitch[o] = pitch_of(p->ow[o]);
 
     auto fail = [&](int code, const char* why) { if (p->status == SIFT_GPU_OK) { p->status = code; p->why = why; } };
     auto check_blur = [&](const BlurSpec& b, int w, int h) {
         if (w < b.r + 1 || h < b.r + 1) fail(SIFT_GPU_E_PRECONDITION, "separableConvolveX/Y(): kernel longer than line");
-        if (b.r > kMaxTileRadius) fail(SIFT_GPU_E_UNSUPPORTED, "blur radius exceeds the tile kernel's shared memory");
+        if (b.r > max_generic_radius() && !stream_box_width(b.r)) fail(SIFT_GPU_E_UNSUPPORTED, "blur radius exceeds the tile kernel's shared memory");
     };
     if (in_w < 1 || in_h < 1) fail(SIFT_GPU_E_INVALID, "empty image");
     if (c->prm.subpixel) {
@@ -354,7 +360,14 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
         return off;
     };
     if (c->prm.subpixel) { p->up_mx = push_map(in_w, in_w * 2); p->up_my = push_map(in_h, in_h * 2); }
-    for (int o = 0; o + 1 < O; ++o) { p->red_mx[o] = push_map(p->ow[o], p->ow[o + 1]); p->red_my[o] = push_map(p->oh[o], p->oh[o + 1]); }
+    auto push_inverse = [&](int n_old, int n_new) {  // source index -> destination index, or -1
+        size_t off = maps.size();
+        std::vector<int> m = resize_index_map(n_old, n_new), inv((size_t)n_old, -1);
+        for (int i = 0; i < n_new; ++i) inv[(size_t)m[(size_t)i]] = i;
+        maps.insert(maps.end(), inv.begin(), inv.end());
+        return off;
+    };
+    for (int o = 0; o + 1 < O; ++o) { p->sel_x[o] = push_inverse(p->ow[o], p->ow[o + 1]); p->sel_y[o] = push_inverse(p->oh[o], p->oh[o + 1]); }
     if (!maps.empty()) {
         if (cudaMalloc(&p->d_maps, sizeof(int) * maps.size()) != cudaSuccess ||
             cudaMemcpy(p->d_maps, maps.data(), sizeof(int) * maps.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -369,6 +382,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
             ScanLayer L{};
             L.d0 = c->d_dog[e][i - 1]; L.d1 = c->d_dog[e][i]; L.d2 = c->d_dog[e][i + 1];
             L.stride = c->maxP[e];
+            L.pitch = p->pitch[e];
             L.w = p->ow[e]; L.h = p->oh[e];
             L.n_yw = (L.h + 31) / 32;
             L.mask_off = mask_off; L.col_base = col_base;
@@ -390,7 +404,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
                 if (p->targets_host[s].base == c->d_gauss[to][ti]) slot = (int)s;
             if (slot < 0) {
                 slot = (int)p->targets_host.size();
-                p->targets_host.push_back(LevelRef{c->d_gauss[to][ti], c->maxP[to], p->ow[to], p->oh[to]});
+                p->targets_host.push_back(LevelRef{c->d_gauss[to][ti], c->maxP[to], p->pitch[to], p->ow[to], p->oh[to]});
                 p->target_octave.push_back(to);
             }
             p->class_target[(size_t)(e * D + i)] = slot;
@@ -400,6 +414,23 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
         cudaMalloc(&p->targets_dev, sizeof(LevelRef) * p->targets_host.size()) != cudaSuccess ||
         cudaMemcpy(p->targets_dev, p->targets_host.data(), sizeof(LevelRef) * p->targets_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
         fail(SIFT_GPU_E_CUDA, "plan upload failed");
+    // TMA descriptors (box width depends on the blur radius); a missing descriptor only means the generic kernel runs
+    auto mk = [&](CUtensorMap* m, const float* base, int w, int h, int pitch, size_t stride, int r) {
+        const int bw = stream_box_width(r);
+        return bw > 0 && tma::make_image_map(m, base, w, h, c->B, (size_t)pitch, stride, bw);
+    };
+    if (c->prm.subpixel) {
+        p->has_up = mk(&p->map_up, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->up_blur.r);
+        p->has_base = mk(&p->map_base, c->d_up, p->ow[0], p->oh[0], p->pitch[0], c->maxP[0], c->base_blur.r);
+    } else {
+        p->has_base = mk(&p->map_base, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->base_blur.r);
+    }
+    for (int o = 0; o < O; ++o) {
+        for (int j = 1; j <= D; ++j)
+            p->has_chain[o][j] = mk(&p->map_chain[o][j], c->d_gauss[o][j - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->chain_blur[o][j].r);
+        if (o < O - 1)
+            p->has_reduce[o] = mk(&p->map_reduce[o], c->d_gauss[o][D - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->reduce_blur[o].r);
+    }
     return p;
 }
 
@@ -407,11 +438,12 @@ static int alloc_buffers(sift_gpu_ctx* c) {
     const int O = c->O, D = c->D, B = c->B;
     int ow[kMaxOctaves], oh[kMaxOctaves];
     octave_dims(c, c->max_in_w, c->max_in_h, ow, oh);
-    c->max_in_px = level_px(c->max_in_w, c->max_in_h);
+    c->max_in_pitch = pitch_of(c->max_in_w);
+    c->max_in_px = level_px(c->max_in_pitch, c->max_in_h);
     size_t cand_cap = 0, mask_cap = 0, col_cap = 0;
     for (int o = 0; o < O; ++o) {
-        c->maxP[o] = level_px(ow[o], oh[o]);
-        cand_cap += c->maxP[o] * (size_t)(D - 2);
+        c->maxP[o] = level_px(pitch_of(ow[o]), oh[o]);
+        cand_cap += level_px(ow[o], oh[o]) * (size_t)(D - 2);
         mask_cap += (size_t)((oh[o] + 31) / 32 + 1) * (size_t)ow[o] * (size_t)(D - 2);
         col_cap += (size_t)ow[o] * (size_t)(D - 2);
     }
@@ -422,7 +454,6 @@ static int alloc_buffers(sift_gpu_ctx* c) {
         CTX_CUDA(cudaMalloc(&c->d_up_tmp, sizeof(float) * c->max_in_px * (size_t)B));
         CTX_CUDA(cudaMalloc(&c->d_up, sizeof(float) * c->maxP[0] * (size_t)B));
     }
-    CTX_CUDA(cudaMalloc(&c->d_scratch, sizeof(float) * c->maxP[0] * (size_t)B));
     for (int o = 0; o < O; ++o) {
         for (int i = 0; i <= D; ++i) CTX_CUDA(cudaMalloc(&c->d_gauss[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
         for (int i = 0; i < D; ++i) CTX_CUDA(cudaMalloc(&c->d_dog[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
@@ -495,12 +526,15 @@ static float* take_desc_block(sift_gpu_ctx* c, size_t floats) {
 }
 
 // ---- device passes ------------------------------------------------------------------------------
-static BlurArgs blur_args(const sift_gpu_ctx* c, const BlurSpec& b, const float* src, size_t sstride, float* dst,
-                          size_t dstride, float* dog, size_t gstride, int w, int h) {
+static BlurArgs blur_args(const sift_gpu_ctx* c, const std::vector<float>& host_taps, const BlurSpec& b, const float* src,
+                          size_t sstride, int spitch, float* dst, size_t dstride, int dpitch, float* dog, size_t gstride, int gpitch,
+                          int w, int h, const CUtensorMap* map) {
     BlurArgs a{};
     a.src = src; a.dst = dst; a.dog = dog;
     a.src_stride = sstride; a.dst_stride = dstride; a.dog_stride = gstride;
-    a.w = w; a.h = h; a.taps = c->d_taps + b.tap_off; a.r = b.r;
+    a.src_pitch = spitch; a.dst_pitch = dpitch; a.dog_pitch = gpitch;
+    a.w = w; a.h = h; a.taps = c->d_taps + b.tap_off; a.taps_host = host_taps.data() + b.tap_off; a.r = b.r;
+    a.map = map;
     return a;
 }
 
@@ -509,25 +543,33 @@ static int run_pyramid(sift_gpu_ctx* c, const Plan* p, int nb) {
     const int O = c->O, D = c->D;
     uint64_t* L = &c->tm.kernel_launches;
     cudaStream_t s = c->stream;
+    const std::vector<float>& ht = c->h_taps;
     const float* base_src = c->d_in;
     size_t base_stride = c->max_in_px;
+    int base_pitch = p->in_pitch;
     if (c->prm.subpixel) {
-        CTX_TRY(launch_blur(blur_args(c, c->up_blur, c->d_in, c->max_in_px, c->d_up_tmp, c->max_in_px, nullptr, 0, p->in_w, p->in_h), nb, c->fma, s, L));
-        CTX_TRY(launch_resize_nn(c->d_up_tmp, c->max_in_px, p->in_w, p->in_h, c->d_up, c->maxP[0], p->ow[0], p->oh[0],
+        CTX_TRY(launch_blur(blur_args(c, ht, c->up_blur, c->d_in, c->max_in_px, p->in_pitch, c->d_up_tmp, c->max_in_px, p->in_pitch, nullptr, 0, 0,
+                                      p->in_w, p->in_h, p->has_up ? &p->map_up : nullptr), nb, c->fma, s, L));
+        CTX_TRY(launch_resize_nn(c->d_up_tmp, c->max_in_px, p->in_pitch, c->d_up, c->maxP[0], p->pitch[0], p->ow[0], p->oh[0],
                                  p->d_maps + p->up_mx, p->d_maps + p->up_my, nb, s, L));
         base_src = c->d_up;
         base_stride = c->maxP[0];
+        base_pitch = p->pitch[0];
     }
-    CTX_TRY(launch_blur(blur_args(c, c->base_blur, base_src, base_stride, c->d_gauss[0][0], c->maxP[0], nullptr, 0, p->ow[0], p->oh[0]), nb, c->fma, s, L));
+    CTX_TRY(launch_blur(blur_args(c, ht, c->base_blur, base_src, base_stride, base_pitch, c->d_gauss[0][0], c->maxP[0], p->pitch[0], nullptr, 0, 0,
+                                  p->ow[0], p->oh[0], p->has_base ? &p->map_base : nullptr), nb, c->fma, s, L));
     for (int o = 0; o < O; ++o) {
         for (int j = 1; j <= D; ++j)
-            CTX_TRY(launch_blur(blur_args(c, c->chain_blur[o][j], c->d_gauss[o][j - 1], c->maxP[o], c->d_gauss[o][j], c->maxP[o],
-                                          c->d_dog[o][j - 1], c->maxP[o], p->ow[o], p->oh[o]), nb, c->fma, s, L));
+            CTX_TRY(launch_blur(blur_args(c, ht, c->chain_blur[o][j], c->d_gauss[o][j - 1], c->maxP[o], p->pitch[o], c->d_gauss[o][j], c->maxP[o],
+                                          p->pitch[o], c->d_dog[o][j - 1], c->maxP[o], p->pitch[o], p->ow[o], p->oh[o],
+                                          p->has_chain[o][j] ? &p->map_chain[o][j] : nullptr), nb, c->fma, s, L));
         if (o < O - 1) {
-            CTX_TRY(launch_blur(blur_args(c, c->reduce_blur[o], c->d_gauss[o][D - 1], c->maxP[o], c->d_scratch, c->maxP[0], nullptr, 0,
-                                          p->ow[o], p->oh[o]), nb, c->fma, s, L));
-            CTX_TRY(launch_resize_nn(c->d_scratch, c->maxP[0], p->ow[o], p->oh[o], c->d_gauss[o + 1][0], c->maxP[o + 1], p->ow[o + 1],
-                                     p->oh[o + 1], p->d_maps + p->red_mx[o], p->d_maps + p->red_my[o], nb, s, L));
+            // alg::reduceToNextLevel: blur with the level's own label sigma, keep only the pixels the resize picks
+            BlurArgs a = blur_args(c, ht, c->reduce_blur[o], c->d_gauss[o][D - 1], c->maxP[o], p->pitch[o], c->d_gauss[o + 1][0], c->maxP[o + 1],
+                                   p->pitch[o + 1], nullptr, 0, 0, p->ow[o], p->oh[o], p->has_reduce[o] ? &p->map_reduce[o] : nullptr);
+            a.sel_x = p->d_maps + p->sel_x[o];
+            a.sel_y = p->d_maps + p->sel_y[o];
+            CTX_TRY(launch_blur(a, nb, c->fma, s, L));
         }
     }
     return 0;
@@ -630,7 +672,6 @@ static int run_chunk(sift_gpu_ctx* c, Plan* p, const std::vector<ChunkImage>& im
     const int nb = (int)imgs.size();
     cudaStream_t s = c->stream;
     uint64_t* L = &c->tm.kernel_launches;
-    const size_t in_px = level_px(p->in_w, p->in_h);
     c->last_plan = p;
     c->last_batch = nb;
 
@@ -643,10 +684,10 @@ static int run_chunk(sift_gpu_ctx* c, Plan* p, const std::vector<ChunkImage>& im
         void* dst = im.dtype == SIFT_GPU_DTYPE_U8 ? (void*)(c->d_in_u8 + (size_t)b * c->max_in_px)
                                                   : (void*)(c->d_in + (size_t)b * c->max_in_px);
         const cudaMemcpyKind kind = im.memory == SIFT_GPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)im.width * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
+        CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->in_pitch * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
     }
     if (imgs[0].img->dtype == SIFT_GPU_DTYPE_U8)
-        CTX_TRY(launch_u8_to_f32(c->d_in_u8, c->max_in_px, c->d_in, c->max_in_px, in_px, nb, s, L));
+        CTX_TRY(launch_u8_to_f32(c->d_in_u8, c->max_in_px, p->in_pitch, c->d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, nb, s, L));
     CTX_CUDA(cudaEventRecord(c->ev[1], s));
     CTX_TRY(run_pyramid(c, p, nb));
     CTX_CUDA(cudaEventRecord(c->ev[2], s));
@@ -669,8 +710,8 @@ static int run_chunk(sift_gpu_ctx* c, Plan* p, const std::vector<ChunkImage>& im
     if (c->prm.subpixel && (c->prm.flags & SIFT_GPU_FLAG_KEEP_UPSAMPLED))
         for (int b = 0; b < nb; ++b)
             if (imgs[(size_t)b].img->upsampled_out)
-                CTX_CUDA(cudaMemcpyAsync(imgs[(size_t)b].img->upsampled_out, c->d_up + (size_t)b * c->maxP[0],
-                                         sizeof(float) * level_px(p->ow[0], p->oh[0]), cudaMemcpyDeviceToHost, s));
+                CTX_CUDA(cudaMemcpy2DAsync(imgs[(size_t)b].img->upsampled_out, sizeof(float) * (size_t)p->ow[0], c->d_up + (size_t)b * c->maxP[0],
+                                           sizeof(float) * (size_t)p->pitch[0], sizeof(float) * (size_t)p->ow[0], (size_t)p->oh[0], cudaMemcpyDeviceToHost, s));
     CTX_CUDA(cudaEventRecord(c->ev[5], s));
     CTX_CUDA(cudaStreamSynchronize(s));
 
@@ -849,7 +890,7 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
         cudaFree(p->d_maps); cudaFree(p->layers_dev); cudaFree(p->targets_dev);
         delete p;
     }
-    cudaFree(c->d_taps); cudaFree(c->d_in_u8); cudaFree(c->d_in); cudaFree(c->d_up_tmp); cudaFree(c->d_up); cudaFree(c->d_scratch);
+    cudaFree(c->d_taps); cudaFree(c->d_in_u8); cudaFree(c->d_in); cudaFree(c->d_up_tmp); cudaFree(c->d_up);
     for (int o = 0; o < kMaxOctaves; ++o)
         for (int i = 0; i < kMaxGauss; ++i) { cudaFree(c->d_gauss[o][i]); cudaFree(c->d_dog[o][i]); }
     cudaFree(c->d_mask); cudaFree(c->d_col_count); cudaFree(c->d_col_off); cudaFree(c->d_cands); cudaFree(c->d_surv);
@@ -937,7 +978,8 @@ int sift_gpu_debug_get_level(sift_gpu_ctx* c, int image_idx, int octave, int ele
     if (width) *width = p->ow[octave];
     if (height) *height = p->oh[octave];
     if (scale) *scale = kind == SIFT_GPU_KIND_DOG ? c->d_scale[octave][elem] : c->g_scale[octave][elem];
-    if (out) CTX_CUDA(cudaMemcpy(out, src, sizeof(float) * level_px(p->ow[octave], p->oh[octave]), cudaMemcpyDeviceToHost));
+    if (out) CTX_CUDA(cudaMemcpy2D(out, sizeof(float) * (size_t)p->ow[octave], src, sizeof(float) * (size_t)p->pitch[octave],
+                                   sizeof(float) * (size_t)p->ow[octave], (size_t)p->oh[octave], cudaMemcpyDeviceToHost));
     return SIFT_GPU_OK;
 }
 
@@ -953,37 +995,56 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
     int r = 0;
     std::vector<float> taps = gaussian_taps(sigma, &r);
     if (w < r + 1 || h < r + 1) return set_error(c, SIFT_GPU_E_PRECONDITION, "separableConvolveX/Y(): kernel longer than line");
-    if (r > kMaxTileRadius) return set_error(c, SIFT_GPU_E_UNSUPPORTED, "radius too large");
+    if (r > max_generic_radius() && !stream_box_width(r)) return set_error(c, SIFT_GPU_E_UNSUPPORTED, "radius too large");
     int dw = w, dh = h;
     if (mode == 1) { dw = (w + 1) / 2; dh = (h + 1) / 2; }
     if (mode == 2) { dw = 2 * w; dh = 2 * h; }
     if (mode != 0 && !(w > 1 && h > 1 && dw > 1 && dh > 1)) return set_error(c, SIFT_GPU_E_PRECONDITION, "resizeImageNoInterpolation(): image too small");
-    float *d_src = nullptr, *d_dst = nullptr, *d_taps = nullptr, *d_out = nullptr;
+    const int sp = pitch_of(w), dp = pitch_of(dw);
+    float *d_src = nullptr, *d_blur = nullptr, *d_taps = nullptr, *d_out = nullptr;
     int* d_map = nullptr;
-    const size_t n = level_px(w, h);
-    int rc = upload(c, src, n, &d_src);
-    if (!rc) rc = upload(c, taps.data(), taps.size(), &d_taps);
-    if (!rc && cudaMalloc(&d_dst, sizeof(float) * n) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    int rc = 0;
+    auto cu = [&](cudaError_t e) { if (e != cudaSuccess && !rc) rc = cuda_fail(e, "debug blur", __FILE__, __LINE__); };
+    cu(cudaMalloc(&d_src, sizeof(float) * level_px(sp, h)));
+    cu(cudaMalloc(&d_blur, sizeof(float) * level_px(sp, h)));
+    cu(cudaMalloc(&d_out, sizeof(float) * level_px(dp, dh)));
+    cu(cudaMalloc(&d_taps, sizeof(float) * taps.size()));
+    if (!rc) {
+        cu(cudaMemcpy2D(d_src, sizeof(float) * (size_t)sp, src, sizeof(float) * (size_t)w, sizeof(float) * (size_t)w, (size_t)h, cudaMemcpyHostToDevice));
+        cu(cudaMemcpy(d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice));
+    }
+    CUtensorMap map;
+    const int bw = stream_box_width(r);
+    const bool has_map = !rc && bw > 0 && tma::make_image_map(&map, d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw);
     if (!rc) {
         BlurArgs a{};
-        a.src = d_src; a.dst = d_dst; a.w = w; a.h = h; a.taps = d_taps; a.r = r;
-        rc = launch_blur(a, 1, c->fma, c->stream, nullptr);
+        a.src = d_src; a.src_pitch = sp; a.w = w; a.h = h; a.taps = d_taps; a.taps_host = taps.data(); a.r = r;
+        a.map = has_map ? &map : nullptr;
+        if (mode == 1) {
+            // reduceToNextLevel: decimation fused into the blur epilogue
+            std::vector<int> mx = resize_index_map(w, dw), my = resize_index_map(h, dh), inv((size_t)(w + h), -1);
+            for (int i = 0; i < dw; ++i) inv[(size_t)mx[(size_t)i]] = i;
+            for (int i = 0; i < dh; ++i) inv[(size_t)(w + my[(size_t)i])] = i;
+            cu(cudaMalloc(&d_map, sizeof(int) * inv.size()));
+            if (!rc) cu(cudaMemcpy(d_map, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice));
+            a.dst = d_out; a.dst_pitch = dp; a.sel_x = d_map; a.sel_y = d_map + w;
+            if (!rc) rc = launch_blur(a, 1, c->fma, c->stream, nullptr);
+        } else {
+            a.dst = mode == 0 ? d_out : d_blur; a.dst_pitch = sp;
+            rc = launch_blur(a, 1, c->fma, c->stream, nullptr);
+            if (!rc && mode == 2) {
+                std::vector<int> both = resize_index_map(w, dw), my = resize_index_map(h, dh);
+                both.insert(both.end(), my.begin(), my.end());
+                cu(cudaMalloc(&d_map, sizeof(int) * both.size()));
+                if (!rc) cu(cudaMemcpy(d_map, both.data(), sizeof(int) * both.size(), cudaMemcpyHostToDevice));
+                if (!rc) rc = launch_resize_nn(d_blur, 0, sp, d_out, 0, dp, dw, dh, d_map, d_map + dw, 1, c->stream, nullptr);
+            }
+        }
     }
-    const float* result = d_dst;
-    if (!rc && mode != 0) {
-        std::vector<int> mx = resize_index_map(w, dw), my = resize_index_map(h, dh);
-        std::vector<int> both(mx);
-        both.insert(both.end(), my.begin(), my.end());
-        if (cudaMalloc(&d_map, sizeof(int) * both.size()) != cudaSuccess || cudaMalloc(&d_out, sizeof(float) * level_px(dw, dh)) != cudaSuccess ||
-            cudaMemcpy(d_map, both.data(), sizeof(int) * both.size(), cudaMemcpyHostToDevice) != cudaSuccess)
-            rc = SIFT_GPU_E_CUDA;
-        if (!rc) rc = launch_resize_nn(d_dst, 0, w, h, d_out, 0, dw, dh, d_map, d_map + dw, 1, c->stream, nullptr);
-        result = d_out;
-    }
-    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
-    if (!rc && cudaMemcpy(dst, result, sizeof(float) * level_px(dw, dh), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
-    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_taps); cudaFree(d_out); cudaFree(d_map);
-    if (rc == SIFT_GPU_E_CUDA && c->error.empty()) c->error = "CUDA failure in debug blur";
+    if (!rc) cu(cudaStreamSynchronize(c->stream));
+    if (!rc) cu(cudaMemcpy2D(dst, sizeof(float) * (size_t)dw, d_out, sizeof(float) * (size_t)dp, sizeof(float) * (size_t)dw, (size_t)dh, cudaMemcpyDeviceToHost));
+    cudaFree(d_src); cudaFree(d_blur); cudaFree(d_taps); cudaFree(d_out); cudaFree(d_map);
+    if (rc) c->error = g_last_error;
     return rc;
 }
 
@@ -1008,7 +1069,7 @@ static int debug_layers_setup(sift_gpu_ctx* c, DebugLayers& S, const float* d0, 
     const size_t n = level_px(w, h);
     for (int i = 0; i < 3; ++i) CTX_TRY(upload(c, hs[i], n, &S.d[i]));
     S.L.d0 = S.d[0]; S.L.d1 = S.d[1]; S.L.d2 = S.d[2];
-    S.L.stride = 0; S.L.w = w; S.L.h = h; S.L.n_yw = (h + 31) / 32; S.L.mask_off = 0; S.L.col_base = 0; S.L.octave = 0; S.L.index = 1;
+    S.L.stride = 0; S.L.pitch = w; S.L.w = w; S.L.h = h; S.L.n_yw = (h + 31) / 32; S.L.mask_off = 0; S.L.col_base = 0; S.L.octave = 0; S.L.index = 1;
     CTX_CUDA(cudaMalloc(&S.dev, sizeof(ScanLayer)));
     CTX_CUDA(cudaMemcpy(S.dev, &S.L, sizeof(ScanLayer), cudaMemcpyHostToDevice));
     CTX_CUDA(cudaMalloc(&S.mask, sizeof(uint32_t) * (size_t)S.L.n_yw * (size_t)w));
