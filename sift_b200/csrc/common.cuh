@@ -73,7 +73,7 @@ struct BlurArgs {
     int r;
     const int* sel_x; // decimation: destination column of source column x, or -1 (device); null = no decimation
     const int* sel_y;
-    const CUtensorMap* map; // host pointer to the TMA descriptor of src (box = stream_box_width(r)), or null
+    const CUtensorMap* map; // host pointer to two TMA descriptors of src (boxes stream_box_width(r) x 8 and x 1), or null
 };
 
 #define SIFT_CUDA_TRY(expr)                                         \

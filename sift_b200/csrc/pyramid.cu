@@ -16,6 +16,8 @@
 //    __syncthreads per chunk each thread column-filters 8 rows of its own column from the ring.
 //    The main loop is unrolled over the ring period so every shared-memory address is a constant.
 //  * blur_tile_kernel: any radius / tiny images; plain shared-memory tile.
+#include <cmath>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -101,31 +103,43 @@ int max_generic_radius() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming kernel.
+// Streaming kernel.  Every warp is an independent pipeline over its own 64-column strip: no CTA-wide
+// barrier anywhere.  Per 8-row chunk the warp (1) waits for its TMA box (one 8-row box for interior
+// chunks, eight 1-row boxes where rows are reflected at the image top/bottom), (2) patches reflected
+// columns on edge strips, (3) row-filters the 8 x 64 block into its private ring of row-filtered
+// lines (lane = 4 columns x 4 rows, float4 windows in registers), (4) column-filters 8 rows of its
+// two columns (lane = columns 2*lane, 2*lane+1) from the ring and writes dst / DoG with 8-byte stores.
+// The chunk loop is unrolled over the ring period, so every shared-memory address is a constant.
+//
+// Arithmetic: exact mode multiplies with packed FMUL2 (two taps of one output in the row pass, two
+// columns in the column pass) and adds with scalar FADD in the reference's order, so results are
+// bit-identical to separate mulss/addss; FMA mode uses FFMA2 (row pass: even/odd tap partial sums).
 template <int R>
 struct SC {
-    static constexpr int CH = 8;        // rows per chunk = warps per CTA
-    static constexpr int TW = 256;      // strip width = threads per CTA
-    static constexpr int NS = 4;        // staging stages
+    static constexpr int CH = 8;        // rows per chunk
+    static constexpr int WC = 64;       // columns per warp
+    static constexpr int NWARP = 2;     // warps per CTA (adjacent strips); small CTAs pack shared memory better
+    static constexpr int NS = 3;        // staging stages per warp (TMA runs two chunks ahead)
     static constexpr int RPAD = (R + 3) & ~3;
-    static constexpr int SW = (TW + 2 * RPAD <= 288) ? 288 : 320;  // staged floats per row (multiple of 32: 128-B aligned rows)
-    static constexpr int NBOX = SW == 288 ? 3 : 2;
-    static constexpr int BOXW = SW / NBOX;                          // 96 or 160 floats: 128-B multiples
+    static constexpr int SWW = (WC + 2 * RPAD <= 96) ? 96 : 128;   // staged floats per row (128-B multiple)
     static constexpr int RC = ((R + CH - 1) / CH) * CH;             // rows loaded above the first output row
     static constexpr int LAG = (R + RC + CH - 1) / CH;              // chunks between a row entering and its output leaving
-    static constexpr int NEED = (LAG + 2) * CH - RC + R;
-    static constexpr int RING = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : 128);
-    static constexpr int PERIOD = RING / CH;
-    static constexpr int NW = 4 + 2 * RPAD;                         // row-pass window floats per group
+    static constexpr int RING = (LAG + 1) * CH - RC + R <= (LAG + 1) * CH ? (LAG + 1) * CH : (LAG + 2) * CH;  // >= (LAG+1)*CH - RC + R, multiple of CH
+    static constexpr int WL = CH + 2 * R;                           // column-pass window rows
+    static constexpr int NW = 4 + 2 * RPAD;                         // row-pass window floats
     static constexpr int OFF = RPAD - R;
-    static constexpr size_t SMEM = sizeof(float) * (size_t)(NS * CH * SW + RING * TW) + NS * sizeof(uint64_t);
-    static_assert(TW + 2 * RPAD <= SW, "radius too large for the streaming kernel");
-    static_assert(PERIOD % NS == 0, "stage index must be a function of the phase");
+    static constexpr int WARP_FLOATS = NS * CH * SWW + RING * WC;
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(NWARP * WARP_FLOATS) + NWARP * NS * sizeof(uint64_t);
+    static_assert(WC + 2 * RPAD <= SWW, "radius too large for the streaming kernel");
+    static_assert(RING >= (LAG + 1) * CH - RC + R && RING % CH == 0 && RING >= WL, "ring too small");
+    static_assert((CH * SWW * 4) % 128 == 0 && (RING * WC * 4) % 128 == 0, "TMA destinations must stay 128-B aligned");
 };
 
 template <int R>
-struct TapsP {
-    float t[2 * R + 1];
+struct TapsP {           // tk[j] = kernel tap applied to source index x - R + j
+    float2 dup[2 * R + 1];  // (tk[j], tk[j])
+    float2 pe[R];           // (tk[2m], tk[2m+1])
+    float2 po[R];           // (tk[2m+1], tk[2m+2])
 };
 
 struct StreamArgs {
@@ -133,148 +147,225 @@ struct StreamArgs {
     int seg;  // output rows per CTA
 };
 
+// one output of the row pass: sum over j of tk[j] * wv[base + j], ascending j
+template <int R, bool FMA, int BASE, int NWV>
+__device__ __forceinline__ float row_output(const float (&wv)[NWV], const TapsP<R>& tp) {
+    if (FMA) {
+        float2 acc2 = make_float2(0.0f, 0.0f);
+        float lead = 0.0f;
+        if (BASE % 2 == 0) {
+#pragma unroll
+            for (int m = 0; m < R; ++m) acc2 = __ffma2_rn(tp.pe[m], make_float2(wv[BASE + 2 * m], wv[BASE + 2 * m + 1]), acc2);
+            lead = tp.dup[2 * R].x * wv[BASE + 2 * R];
+        } else {
+            lead = tp.dup[0].x * wv[BASE];
+#pragma unroll
+            for (int m = 0; m < R; ++m) acc2 = __ffma2_rn(tp.po[m], make_float2(wv[BASE + 2 * m + 1], wv[BASE + 2 * m + 2]), acc2);
+        }
+        return (acc2.x + acc2.y) + lead;
+    } else {
+        float acc;
+        if (BASE % 2 == 0) {
+            float2 m0 = __fmul2_rn(tp.pe[0], make_float2(wv[BASE], wv[BASE + 1]));
+            acc = __fadd_rn(m0.x, m0.y);
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+                const float2 pm = __fmul2_rn(tp.pe[m], make_float2(wv[BASE + 2 * m], wv[BASE + 2 * m + 1]));
+                acc = __fadd_rn(__fadd_rn(acc, pm.x), pm.y);
+            }
+            acc = __fadd_rn(acc, __fmul_rn(tp.dup[2 * R].x, wv[BASE + 2 * R]));
+        } else {
+            acc = __fmul_rn(tp.dup[0].x, wv[BASE]);
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const float2 pm = __fmul2_rn(tp.po[m], make_float2(wv[BASE + 2 * m + 1], wv[BASE + 2 * m + 2]));
+                acc = __fadd_rn(__fadd_rn(acc, pm.x), pm.y);
+            }
+        }
+        return acc;
+    }
+}
+
+template <bool FMA>
+__device__ __forceinline__ float2 tap_acc2(float2 acc, float2 t, float2 v) {
+    if (FMA) return __ffma2_rn(t, v, acc);
+    // exact: one packed multiply, two scalar adds (a packed add after a packed multiply would be contracted by ptxas)
+    const float2 m = __fmul2_rn(t, v);
+    return make_float2(__fadd_rn(acc.x, m.x), __fadd_rn(acc.y, m.y));
+}
+
+// Reflect patch of one staged chunk (edge strips only): staged column c holds x = xs - rpad + c.  TMA zero-filled
+// what lies outside the image; columns -1..-r and w..w+r-1 get their mirrored pixels, which are staged in the same row
+// (x = -k mirrors to k <= r <= rpad + strip; x = w-1+k mirrors to w-1-k >= xs - rpad because rpad >= r and xs < w).
+__device__ __noinline__ void patch_reflected_columns(float* st, int w, int xs, int rpad, int r, int sww, int lane) {
+    const int n = 2 * r;  // per row: r columns left of 0, r columns right of w-1
+    for (int e = lane; e < 8 * n; e += 32) {
+        const int rr = e / n, k = e - rr * n;
+        const int gx = k < r ? -1 - k : w + (k - r);
+        const int c = gx - (xs - rpad);
+        const int cs = reflect101(gx, w) - (xs - rpad);
+        if (c >= 0 && c < sww && cs >= 0 && cs < sww) st[rr * sww + c] = st[rr * sww + cs];
+    }
+    tma::fence_proxy_async();  // generic-proxy writes above vs. the next TMA write into this stage
+    __syncwarp();
+}
+
+// lane 0: fetch the 8 rows v0..v0+7 of columns [x, x + box) of image b into dst (one box when no row is reflected)
+__device__ __noinline__ void issue_chunk_tma(float* dst, uint64_t* bar, const CUtensorMap* map8, const CUtensorMap* map1, int x, int v0,
+                                             int h, int b, int sww) {
+    tma::mbar_arrive_expect_tx(bar, 8 * sww * (int)sizeof(float));
+    if (v0 >= 0 && v0 + 8 <= h) {
+        tma::load_3d(dst, map8, bar, x, v0, b);
+    } else {
+#pragma unroll 1
+        for (int rr = 0; rr < 8; ++rr) tma::load_3d(dst + rr * sww, map1, bar, x, reflect101(v0 + rr, h), b);
+    }
+}
+
 template <int R, bool FMA, bool DECIMATE>
-__global__ void __launch_bounds__(256) blur_stream_kernel(const __grid_constant__ CUtensorMap map, const StreamArgs sa,
-                                                          const TapsP<R> taps) {
+__global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__ CUtensorMap map8, const __grid_constant__ CUtensorMap map1,
+                                                         const StreamArgs sa, const TapsP<R> taps) {
     using C = SC<R>;
+    static_assert(C::CH == 8, "helpers assume 8-row chunks");
     extern __shared__ __align__(1024) unsigned char smem_raw[];     // TMA destinations must be 128-B aligned
-    float* stage = reinterpret_cast<float*>(smem_raw);            // [NS][CH][SW]
-    float* ring = stage + C::NS * C::CH * C::SW;                  // [RING][TW]
-    uint64_t* full = (uint64_t*)(ring + C::RING * C::TW);         // [NS]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* stage = reinterpret_cast<float*>(smem_raw) + warp * C::WARP_FLOATS;   // [NS][CH][SWW]
+    float* ring = stage + C::NS * C::CH * C::SWW;                                // [RING][WC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + C::NWARP * C::WARP_FLOATS) + warp * C::NS;
 
     const BlurArgs& a = sa.a;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int w = a.w, h = a.h;
-    const int x0 = blockIdx.x * C::TW;
+    const int xs = (blockIdx.x * C::NWARP + warp) * C::WC;   // first column of this warp's strip
+    if (xs >= w) return;                                     // warps are independent: no barrier below
     const int y0 = blockIdx.y * sa.seg;
     const int y1 = min(y0 + sa.seg, h);
     const int n_out_chunks = (y1 - y0 + C::CH - 1) / C::CH;
     const int n_in = n_out_chunks + C::LAG;
-    const bool edge = (x0 - C::RPAD < 0) || (x0 - C::RPAD + C::SW > w);
+    const bool edge = (xs - C::RPAD < 0) || (xs - C::RPAD + C::SWW > w);
     const float* src = a.src + (size_t)b * a.src_stride;
 
-    if (tid == 0) {
-        tma::prefetch_map(&map);
-        for (int s = 0; s < C::NS; ++s) tma::mbar_init(&full[s], C::CH);
+    if (lane == 0) {
+        tma::prefetch_map(&map8);
+        for (int s = 0; s < C::NS; ++s) tma::mbar_init(&full[s], 1);
         tma::fence_barrier_init();
     }
-    __syncthreads();
-
-    // warp `warp` owns staging row `warp` of every chunk: its leader issues the row's TMA boxes
-    auto issue_row = [&](int i, int s) {
-        const int v = y0 - C::RC + i * C::CH + warp;
-        const int sy = reflect101(v, h);
-        float* dst = stage + (s * C::CH + warp) * C::SW;
-        tma::mbar_arrive_expect_tx(&full[s], C::SW * (int)sizeof(float));
-#pragma unroll
-        for (int q = 0; q < C::NBOX; ++q) tma::load_3d(dst + q * C::BOXW, &map, &full[s], x0 - C::RPAD + q * C::BOXW, sy, b);
-    };
+    __syncwarp();
     if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < C::NS; ++i)
-            if (i < n_in) issue_row(i, i);
+        for (int i = 0; i < C::NS && i < n_in; ++i)
+            issue_chunk_tma(stage + i * C::CH * C::SWW, &full[i], &map8, &map1, xs - C::RPAD, y0 - C::RC + i * C::CH, h, b, C::SWW);
     }
 
-    const int x = x0 + tid;              // this thread's column in the column pass
+    // row pass: lane = (row parity, column group): columns 4*cg..4*cg+3 of rows rsub, rsub+2, rsub+4, rsub+6
+    const int cg = lane & 15, rsub = lane >> 4;
+    // column pass: columns xs + 2*lane, +1 (for an odd width the second column lies in the row's padding: pitch % 32 == 0)
+    const int x = xs + 2 * lane;
     const bool active = x < w;
-    int sel_col = -1;
-    if (DECIMATE && active) sel_col = a.sel_x[x];
-    // column bases; per row only a 32-bit y*pitch offset is added
-    float* const dst_col = a.dst ? a.dst + (size_t)b * a.dst_stride + (DECIMATE ? (sel_col >= 0 ? sel_col : 0) : x) : nullptr;
+    int sel0 = -1, sel1 = -1;
+    if (DECIMATE && active) {
+        sel0 = a.sel_x[x];
+        if (x + 1 < w) sel1 = a.sel_x[x + 1];
+    }
+    float* const dst_col = a.dst ? a.dst + (size_t)b * a.dst_stride + (DECIMATE ? 0 : x) : nullptr;
     float* const dog_col = a.dog ? a.dog + (size_t)b * a.dog_stride + x : nullptr;
-    const float* const src_col = src + x;
+    const float* const src_col = src + (active ? x : 0);
+    const float* const ring_col = ring + 2 * lane;
 
-    for (int i0 = 0; i0 < n_in; i0 += C::PERIOD) {
+    // DoG centre values of the next output chunk, fetched one chunk ahead so their latency never shows
+    float2 lower[C::CH];
+    auto fetch_lower = [&](int jn) {
 #pragma unroll
-        for (int p = 0; p < C::PERIOD; ++p) {
-            const int i = i0 + p;
-            if (i < n_in) {
-                const int s = p % C::NS;  // compile-time after unrolling (PERIOD % NS == 0)
-                tma::mbar_wait(&full[s], (uint32_t)((i / C::NS) & 1));
-                float* st = stage + (s * C::CH + warp) * C::SW;
-                if (edge) {
-                    // reflect patch of this warp's row: staged column c holds x = x0 - RPAD + c
-                    const int v = y0 - C::RC + i * C::CH + warp;
-                    const float* srow = src + (size_t)reflect101(v, h) * a.src_pitch;
-                    for (int c = lane; c < C::SW; c += 32) {
-                        const int gx = x0 - C::RPAD + c;
-                        if ((gx < 0 && gx >= -R) || (gx >= w && gx <= w - 1 + R)) st[c] = srow[reflect101(gx, w)];
+        for (int o = 0; o < C::CH; ++o) lower[o] = *reinterpret_cast<const float2*>(src_col + min(y0 + jn * C::CH + o, y1 - 1) * a.src_pitch);
+    };
+    if (!DECIMATE && dog_col) fetch_lower(0);
+
+    int s = 0;                              // staging stage of chunk i and its mbarrier phase parity
+    uint32_t parity = 0;
+    int wslot = 0;                          // ring slot of the chunk being row-filtered
+    int ub = (C::RC - R) % C::RING;         // ring slot of the first window row of the next output chunk
+#pragma unroll 1
+    for (int i = 0; i < n_in; ++i) {
+        float* const st = stage + s * C::CH * C::SWW;
+        tma::mbar_wait(&full[s], parity);
+        if (edge) patch_reflected_columns(st, w, xs, C::RPAD, R, C::SWW, lane);
+        // ---- row pass ----
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int rr = rsub + 2 * q;
+            const float* srow = st + rr * C::SWW + 4 * cg;
+            float wv[C::NW];
+#pragma unroll
+            for (int k = 0; k < C::NW / 4; ++k) {
+                const float4 f = *reinterpret_cast<const float4*>(srow + 4 * k);
+                wv[4 * k] = f.x; wv[4 * k + 1] = f.y; wv[4 * k + 2] = f.z; wv[4 * k + 3] = f.w;
+            }
+            float4 o;
+            o.x = row_output<R, FMA, C::OFF + 0>(wv, taps);
+            o.y = row_output<R, FMA, C::OFF + 1>(wv, taps);
+            o.z = row_output<R, FMA, C::OFF + 2>(wv, taps);
+            o.w = row_output<R, FMA, C::OFF + 3>(wv, taps);
+            *reinterpret_cast<float4*>(ring + (wslot + rr) * C::WC + 4 * cg) = o;
+        }
+        wslot = wslot + C::CH == C::RING ? 0 : wslot + C::CH;
+        __syncwarp();  // ring rows of chunk i visible to the warp; every lane is done with stage s
+        if (lane == 0 && i + C::NS < n_in)
+            issue_chunk_tma(st, &full[s], &map8, &map1, xs - C::RPAD, y0 - C::RC + (i + C::NS) * C::CH, h, b, C::SWW);
+        // ---- column pass for output chunk j = i - LAG ----
+        const int j = i - C::LAG;
+        if (j >= 0) {
+            if (active) {
+                const int yb = y0 + j * C::CH;
+                const int nrows = y1 - yb;  // >= 1; a full chunk unless this is the segment's last one
+                float2 win[C::WL];
+                if (ub + C::WL <= C::RING) {
+                    const float* p0 = ring_col + ub * C::WC;
+#pragma unroll
+                    for (int k = 0; k < C::WL; ++k) win[k] = *reinterpret_cast<const float2*>(p0 + k * C::WC);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < C::WL; ++k) {
+                        int sl = ub + k;
+                        sl = sl >= C::RING ? sl - C::RING : sl;
+                        win[k] = *reinterpret_cast<const float2*>(ring_col + sl * C::WC);
                     }
-                    tma::fence_proxy_async();  // generic-proxy writes above vs. the next TMA write into this row
-                    __syncwarp();
                 }
-                // ---- row pass: two float4 groups per lane, columns 4*lane and 128 + 4*lane ----
+                if (!DECIMATE) {
+                    float2 acc[C::CH];
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int c0 = 4 * lane + 128 * g;
-                    float wv[C::NW];
+                    for (int jj = 0; jj <= 2 * R; ++jj) {
 #pragma unroll
-                    for (int k = 0; k < C::NW / 4; ++k) {
-                        const float4 q = *reinterpret_cast<const float4*>(st + c0 + 4 * k);
-                        wv[4 * k] = q.x; wv[4 * k + 1] = q.y; wv[4 * k + 2] = q.z; wv[4 * k + 3] = q.w;
+                        for (int o = 0; o < C::CH; ++o) acc[o] = jj == 0 ? __fmul2_rn(taps.dup[0], win[o]) : tap_acc2<FMA>(acc[o], taps.dup[jj], win[o + jj]);
                     }
-                    float acc[4];
+                    if (dst_col) {
 #pragma unroll
-                    for (int j = 0; j <= 2 * R; ++j) {
-                        const float t = taps.t[2 * R - j];
-#pragma unroll
-                        for (int o = 0; o < 4; ++o) acc[o] = j == 0 ? __fmul_rn(t, wv[o + C::OFF]) : tap_acc<FMA>(acc[o], t, wv[o + C::OFF + j]);
+                        for (int o = 0; o < C::CH; ++o)
+                            if (o < nrows) *reinterpret_cast<float2*>(dst_col + (yb + o) * a.dst_pitch) = acc[o];
                     }
-                    const int slot = (p * C::CH) % C::RING;  // + warp (< CH) never wraps: RING is a multiple of CH
-                    *reinterpret_cast<float4*>(ring + (slot + warp) * C::TW + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                }
-                __syncthreads();  // ring rows of chunk i visible; every lane of this warp is done with staging row (s, warp)
-                if (lane == 0 && i + C::NS < n_in) issue_row(i + C::NS, s);
-                // ---- column pass for output chunk j = i - LAG ----
-                const int j = i - C::LAG;
-                if (j >= 0 && active) {
-                    const int ub = ((((p - C::LAG) * C::CH + C::RC - R) % C::RING) + C::RING) % C::RING;  // compile-time after unrolling
-                    const int yb = y0 + j * C::CH;
-                    if (!DECIMATE) {
-                        float win[C::CH + 2 * R];
+                    if (dog_col) {
 #pragma unroll
-                        for (int k = 0; k < C::CH + 2 * R; ++k) win[k] = ring[((ub + k) % C::RING) * C::TW + tid];
-                        float acc[C::CH];
+                        for (int o = 0; o < C::CH; ++o)
+                            if (o < nrows)
+                                *reinterpret_cast<float2*>(dog_col + (yb + o) * a.dog_pitch) =
+                                    make_float2(__fadd_rn(128.0f, __fsub_rn(acc[o].x, lower[o].x)), __fadd_rn(128.0f, __fsub_rn(acc[o].y, lower[o].y)));
+                        if (j + 1 < n_out_chunks) fetch_lower(j + 1);
+                    }
+                } else {
 #pragma unroll
-                        for (int jj = 0; jj <= 2 * R; ++jj) {
-                            const float t = taps.t[2 * R - jj];
+                    for (int o = 0; o < C::CH; ++o) {
+                        const int sy = o < nrows ? a.sel_y[yb + o] : -1;  // uniform across the warp
+                        if (sy >= 0) {
+                            float2 acc = __fmul2_rn(taps.dup[0], win[o]);
 #pragma unroll
-                            for (int o = 0; o < C::CH; ++o) acc[o] = jj == 0 ? __fmul_rn(t, win[o]) : tap_acc<FMA>(acc[o], t, win[o + jj]);
-                        }
-                        const int nrows = y1 - yb;  // >= 1; a full chunk unless this is the segment's last one
-                        if (dst_col) {
-#pragma unroll
-                            for (int o = 0; o < C::CH; ++o)
-                                if (o < nrows) dst_col[(yb + o) * a.dst_pitch] = acc[o];
-                        }
-                        if (dog_col) {
-                            float lower[C::CH];
-#pragma unroll
-                            for (int o = 0; o < C::CH; ++o) lower[o] = o < nrows ? src_col[(yb + o) * a.src_pitch] : 0.0f;
-#pragma unroll
-                            for (int o = 0; o < C::CH; ++o)
-                                if (o < nrows) dog_col[(yb + o) * a.dog_pitch] = __fadd_rn(128.0f, __fsub_rn(acc[o], lower[o]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int o = 0; o < C::CH; ++o) {
-                            const int y = yb + o;
-                            const int sy = y < y1 ? a.sel_y[y] : -1;  // uniform across the CTA
-                            if (sy >= 0) {
-                                float acc = 0.0f;
-#pragma unroll
-                                for (int jj = 0; jj <= 2 * R; ++jj) {
-                                    const float v = ring[((ub + o + jj) % C::RING) * C::TW + tid];
-                                    acc = jj == 0 ? __fmul_rn(taps.t[2 * R], v) : tap_acc<FMA>(acc, taps.t[2 * R - jj], v);
-                                }
-                                if (sel_col >= 0) dst_col[sy * a.dst_pitch] = acc;
-                            }
+                            for (int jj = 1; jj <= 2 * R; ++jj) acc = tap_acc2<FMA>(acc, taps.dup[jj], win[o + jj]);
+                            if (sel0 >= 0) dst_col[sy * a.dst_pitch + sel0] = acc.x;
+                            if (sel1 >= 0) dst_col[sy * a.dst_pitch + sel1] = acc.y;
                         }
                     }
                 }
             }
+            ub = ub + C::CH >= C::RING ? ub + C::CH - C::RING : ub + C::CH;
         }
+        if (++s == C::NS) { s = 0; parity ^= 1u; }
     }
 }
 
@@ -283,17 +374,58 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
     using C = SC<R>;
     StreamArgs sa;
     sa.a = a;
-    // rows per CTA: enough CTAs for ~2 waves when the batch allows, never less than 64 rows (halo amortisation)
-    const int strips = (a.w + C::TW - 1) / C::TW;
-    int segs = (2 * 148 * 2 + strips * batch - 1) / (strips * batch);
-    int seg = (a.h + segs - 1) / segs;
-    if (seg < 64) seg = 64;
-    seg = (seg + C::CH - 1) / C::CH * C::CH;
-    if (seg > a.h) seg = (a.h + C::CH - 1) / C::CH * C::CH;
+    // Rows per CTA.  More segments = more parallelism but RC + R extra rows to stage and row-filter per segment; fewer
+    // segments = less overhead but a ragged last wave.  Pick the count with the best (last-wave fill) / (halo overhead).
+    const int strips = (a.w + C::NWARP * C::WC - 1) / (C::NWARP * C::WC);
+    static int ctas_per_sm[2][2] = {{0, 0}, {0, 0}};
+    int& cps = ctas_per_sm[fma ? 1 : 0][a.sel_x ? 1 : 0];
+    if (cps == 0) {
+        int n = 0;
+        cudaError_t e;
+        // the occupancy query needs the opt-in shared-memory limit to be raised first
+        cudaFuncSetAttribute(blur_stream_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(blur_stream_kernel<R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(blur_stream_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(blur_stream_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (fma) e = a.sel_x ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, true, true>, C::NWARP * 32, C::SMEM)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, true, false>, C::NWARP * 32, C::SMEM);
+        else e = a.sel_x ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, false, true>, C::NWARP * 32, C::SMEM)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, false, false>, C::NWARP * 32, C::SMEM);
+        cps = (e == cudaSuccess && n > 0) ? n : 1;
+        (void)cudaGetLastError();
+    }
+    int n_sm = 148;
+    {
+        static int cached_sm = 0;
+        if (!cached_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&cached_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cached_sm <= 0) cached_sm = 148;
+        }
+        n_sm = cached_sm;
+    }
+    const double slots = (double)n_sm * cps;
+    int seg = a.h;
+    double best = -1.0;
+    for (int nseg = 1; nseg <= (a.h + 15) / 16; ++nseg) {
+        int sg = ((a.h + nseg - 1) / nseg + C::CH - 1) / C::CH * C::CH;
+        const int real_segs = (a.h + sg - 1) / sg;
+        const double tiles = (double)strips * real_segs * batch;
+        const double waves = std::ceil(tiles / slots);
+        const double fill = tiles / (waves * slots);
+        const double overhead = (double)(sg + C::RC + R + C::LAG * C::CH * 0.25) / sg;
+        const double score = fill / overhead;
+        if (score > best + 1e-9) { best = score; seg = sg; }
+    }
     sa.seg = seg;
     dim3 grid(strips, (a.h + seg - 1) / seg, batch);
     TapsP<R> tp;
-    for (int i = 0; i < 2 * R + 1; ++i) tp.t[i] = a.taps_host[i];
+    auto tk = [&](int j) { return a.taps_host[2 * R - j]; };  // kernel walked from +r down while the source index ascends
+    for (int j = 0; j < 2 * R + 1; ++j) tp.dup[j] = make_float2(tk(j), tk(j));
+    for (int m = 0; m < R; ++m) {
+        tp.pe[m] = make_float2(tk(2 * m), tk(2 * m + 1));
+        tp.po[m] = make_float2(tk(2 * m + 1), tk(2 * m + 2));
+    }
     const bool dec = a.sel_x != nullptr;
 #define LAUNCH(F, D)                                                                                                        \
     do {                                                                                                                    \
@@ -302,7 +434,7 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
             SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_stream_kernel<R, F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM)); \
             attr = true;                                                                                                    \
         }                                                                                                                   \
-        blur_stream_kernel<R, F, D><<<grid, 256, C::SMEM, s>>>(*a.map, sa, tp);                                             \
+        blur_stream_kernel<R, F, D><<<grid, C::NWARP * 32, C::SMEM, s>>>(a.map[0], a.map[1], sa, tp);                       \
     } while (0)
     if (fma) { if (dec) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (dec) LAUNCH(false, true); else LAUNCH(false, false); }
@@ -313,12 +445,12 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
 
 int stream_box_width(int r) {
     switch (r) {
-        case 3: return SC<3>::BOXW;
-        case 5: return SC<5>::BOXW;
-        case 7: return SC<7>::BOXW;
-        case 10: return SC<10>::BOXW;
-        case 14: return SC<14>::BOXW;
-        case 19: return SC<19>::BOXW;
+        case 3: return SC<3>::SWW;
+        case 5: return SC<5>::SWW;
+        case 7: return SC<7>::SWW;
+        case 10: return SC<10>::SWW;
+        case 14: return SC<14>::SWW;
+        case 19: return SC<19>::SWW;
         default: return 0;
     }
 }

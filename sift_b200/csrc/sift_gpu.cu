@@ -141,7 +141,7 @@ struct Plan {
     int in_w = 0, in_h = 0, in_pitch = 0;
     int ow[kMaxOctaves] = {0}, oh[kMaxOctaves] = {0}, pitch[kMaxOctaves] = {0};
     // TMA descriptors of the blur sources (valid[] says whether the streaming kernel can be used)
-    CUtensorMap map_up, map_base, map_chain[kMaxOctaves][kMaxGauss], map_reduce[kMaxOctaves];
+    CUtensorMap map_up[2], map_base[2], map_chain[kMaxOctaves][kMaxGauss][2], map_reduce[kMaxOctaves][2];  // [0]: 8-row box, [1]: 1-row box
     bool has_up = false, has_base = false, has_chain[kMaxOctaves][kMaxGauss] = {{false}}, has_reduce[kMaxOctaves] = {false};
     size_t sel_x[kMaxOctaves] = {0}, sel_y[kMaxOctaves] = {0};  // decimation: inverse index maps (offsets into d_maps)
     int status = SIFT_GPU_OK;
@@ -417,19 +417,20 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
     // TMA descriptors (box width depends on the blur radius); a missing descriptor only means the generic kernel runs
     auto mk = [&](CUtensorMap* m, const float* base, int w, int h, int pitch, size_t stride, int r) {
         const int bw = stream_box_width(r);
-        return bw > 0 && tma::make_image_map(m, base, w, h, c->B, (size_t)pitch, stride, bw);
+        return bw > 0 && tma::make_image_map(&m[0], base, w, h, c->B, (size_t)pitch, stride, bw, 8) &&
+               tma::make_image_map(&m[1], base, w, h, c->B, (size_t)pitch, stride, bw, 1);
     };
     if (c->prm.subpixel) {
-        p->has_up = mk(&p->map_up, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->up_blur.r);
-        p->has_base = mk(&p->map_base, c->d_up, p->ow[0], p->oh[0], p->pitch[0], c->maxP[0], c->base_blur.r);
+        p->has_up = mk(p->map_up, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->up_blur.r);
+        p->has_base = mk(p->map_base, c->d_up, p->ow[0], p->oh[0], p->pitch[0], c->maxP[0], c->base_blur.r);
     } else {
-        p->has_base = mk(&p->map_base, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->base_blur.r);
+        p->has_base = mk(p->map_base, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->base_blur.r);
     }
     for (int o = 0; o < O; ++o) {
         for (int j = 1; j <= D; ++j)
-            p->has_chain[o][j] = mk(&p->map_chain[o][j], c->d_gauss[o][j - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->chain_blur[o][j].r);
+            p->has_chain[o][j] = mk(p->map_chain[o][j], c->d_gauss[o][j - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->chain_blur[o][j].r);
         if (o < O - 1)
-            p->has_reduce[o] = mk(&p->map_reduce[o], c->d_gauss[o][D - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->reduce_blur[o].r);
+            p->has_reduce[o] = mk(p->map_reduce[o], c->d_gauss[o][D - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->reduce_blur[o].r);
     }
     return p;
 }
@@ -549,7 +550,7 @@ static int run_pyramid(sift_gpu_ctx* c, const Plan* p, int nb) {
     int base_pitch = p->in_pitch;
     if (c->prm.subpixel) {
         CTX_TRY(launch_blur(blur_args(c, ht, c->up_blur, c->d_in, c->max_in_px, p->in_pitch, c->d_up_tmp, c->max_in_px, p->in_pitch, nullptr, 0, 0,
-                                      p->in_w, p->in_h, p->has_up ? &p->map_up : nullptr), nb, c->fma, s, L));
+                                      p->in_w, p->in_h, p->has_up ? p->map_up : nullptr), nb, c->fma, s, L));
         CTX_TRY(launch_resize_nn(c->d_up_tmp, c->max_in_px, p->in_pitch, c->d_up, c->maxP[0], p->pitch[0], p->ow[0], p->oh[0],
                                  p->d_maps + p->up_mx, p->d_maps + p->up_my, nb, s, L));
         base_src = c->d_up;
@@ -557,16 +558,16 @@ static int run_pyramid(sift_gpu_ctx* c, const Plan* p, int nb) {
         base_pitch = p->pitch[0];
     }
     CTX_TRY(launch_blur(blur_args(c, ht, c->base_blur, base_src, base_stride, base_pitch, c->d_gauss[0][0], c->maxP[0], p->pitch[0], nullptr, 0, 0,
-                                  p->ow[0], p->oh[0], p->has_base ? &p->map_base : nullptr), nb, c->fma, s, L));
+                                  p->ow[0], p->oh[0], p->has_base ? p->map_base : nullptr), nb, c->fma, s, L));
     for (int o = 0; o < O; ++o) {
         for (int j = 1; j <= D; ++j)
             CTX_TRY(launch_blur(blur_args(c, ht, c->chain_blur[o][j], c->d_gauss[o][j - 1], c->maxP[o], p->pitch[o], c->d_gauss[o][j], c->maxP[o],
                                           p->pitch[o], c->d_dog[o][j - 1], c->maxP[o], p->pitch[o], p->ow[o], p->oh[o],
-                                          p->has_chain[o][j] ? &p->map_chain[o][j] : nullptr), nb, c->fma, s, L));
+                                          p->has_chain[o][j] ? p->map_chain[o][j] : nullptr), nb, c->fma, s, L));
         if (o < O - 1) {
             // alg::reduceToNextLevel: blur with the level's own label sigma, keep only the pixels the resize picks
             BlurArgs a = blur_args(c, ht, c->reduce_blur[o], c->d_gauss[o][D - 1], c->maxP[o], p->pitch[o], c->d_gauss[o + 1][0], c->maxP[o + 1],
-                                   p->pitch[o + 1], nullptr, 0, 0, p->ow[o], p->oh[o], p->has_reduce[o] ? &p->map_reduce[o] : nullptr);
+                                   p->pitch[o + 1], nullptr, 0, 0, p->ow[o], p->oh[o], p->has_reduce[o] ? p->map_reduce[o] : nullptr);
             a.sel_x = p->d_maps + p->sel_x[o];
             a.sel_y = p->d_maps + p->sel_y[o];
             CTX_TRY(launch_blur(a, nb, c->fma, s, L));
@@ -1013,13 +1014,14 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
         cu(cudaMemcpy2D(d_src, sizeof(float) * (size_t)sp, src, sizeof(float) * (size_t)w, sizeof(float) * (size_t)w, (size_t)h, cudaMemcpyHostToDevice));
         cu(cudaMemcpy(d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice));
     }
-    CUtensorMap map;
+    CUtensorMap map[2];
     const int bw = stream_box_width(r);
-    const bool has_map = !rc && bw > 0 && tma::make_image_map(&map, d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw);
+    const bool has_map = !rc && bw > 0 && tma::make_image_map(&map[0], d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw, 8) &&
+                         tma::make_image_map(&map[1], d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw, 1);
     if (!rc) {
         BlurArgs a{};
         a.src = d_src; a.src_pitch = sp; a.w = w; a.h = h; a.taps = d_taps; a.taps_host = taps.data(); a.r = r;
-        a.map = has_map ? &map : nullptr;
+        a.map = has_map ? map : nullptr;
         if (mode == 1) {
             // reduceToNextLevel: decimation fused into the blur epilogue
             std::vector<int> mx = resize_index_map(w, dw), my = resize_index_map(h, dh), inv((size_t)(w + h), -1);

@@ -68,14 +68,14 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 images (w x h, row pitch in elements) of a batch laid out `img_stride` elements apart; box = box_w x 1 x 1.
+// fp32 images (w x h, row pitch in elements) of a batch laid out `img_stride` elements apart; box = box_w x box_h x 1.
 // Out-of-bounds elements are zero-filled.  Returns false when the driver entry point or the encoding fails.
-inline bool make_image_map(CUtensorMap* map, const float* base, int w, int h, int batch, size_t pitch, size_t img_stride, int box_w) {
+inline bool make_image_map(CUtensorMap* map, const float* base, int w, int h, int batch, size_t pitch, size_t img_stride, int box_w, int box_h) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)img_stride * sizeof(float)};
-    cuuint32_t box[3] = {(cuuint32_t)box_w, 1, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if (batch == 1) strides[1] = (cuuint64_t)pitch * sizeof(float) * (cuuint64_t)h;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
