@@ -216,9 +216,20 @@ def run_ours(args):
     wall_d, acc_d, clocks = timed(dev_frames.data_ptr(), capi.MEM_DEVICE)
     wall_h, acc_h, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
 
+    # Roofline of the pyramid + DoG stage: in the pipelined runs above three device passes overlap, so a stage's
+    # CUDA-event duration includes other passes' kernels.  Time the stage on a serial context (one pass at a time,
+    # same kernels, same frames resident in HBM, CUDA events on the library's stream) for the roofline figure.
+    g.close()
+    g = capi.SiftGpu(DPE, OCTAVES, 1.6, capi.SQRT2_F32, False, max_width=W, max_height=H, max_batch=args.device_batch,
+                     device=local_rank, flags=args.flags | capi.FLAG_SERIAL)
+    do_steps(dev_frames.data_ptr(), capi.MEM_DEVICE, 1, 0)
+    torch.cuda.synchronize()
+    n_roof = max(1, min(args.steps, 4))
+    acc_r = do_steps(dev_frames.data_ptr(), capi.MEM_DEVICE, n_roof, 1)
+
     # run() is synchronous (it returns after its last stream sync), so the host clock around the K steps equals the
     # device-side span; span_ms (CUDA events on the library's stream) is reported beside it.  Max over ranks.
-    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_d["pyramid_ms"]],
+    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_r["pyramid_ms"]],
                                     [args.steps * B, acc_d["launches"], acc_d["kps"], acc_d["cands"]])
     if rank != 0:
         g.close()
@@ -235,7 +246,7 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     pyr_bytes = pyramid_bytes(W, H, OCTAVES, DPE, False)
-    achieved = pyr_bytes * args.steps * B / (pyr_ms * 1e-3) / 1e9  # per rank: bytes of this rank's frames / its pyramid time
+    achieved = pyr_bytes * n_roof * B / (pyr_ms * 1e-3) / 1e9  # per rank: bytes of this rank's frames / its pyramid-stage time
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "pyramid_traffic.json"))).get("dram_bytes_per_image")
@@ -259,7 +270,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "pyramid+DoG stage (blur/DoG/decimation launches of one device pass)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "algorithmic_bytes_per_image": pyr_bytes, "pyramid_ms_per_image": pyr_ms / (args.steps * B), "traffic": traffic},
+                     "algorithmic_bytes_per_image": pyr_bytes, "pyramid_ms_per_image": pyr_ms / (n_roof * B),
+                     "measured": "serial context (SIFT_GPU_FLAG_SERIAL), %d steps, CUDA events around the stage" % n_roof, "traffic": traffic,
+                     "serial_stage_ms_per_image": {k2: v / (n_roof * B) for k2, v in acc_r["stages"].items()}},
         "device_span_ms_per_step": span_d / args.steps,
         "stage_ms_per_image": {k2: v / (args.steps * B) for k2, v in acc_d["stages"].items()},
     }
@@ -277,9 +290,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="frames per step per GPU")
     ap.add_argument("--frames", type=int, default=64, help="distinct synthetic frames per GPU (cycled)")
-    ap.add_argument("--device-batch", type=int, default=32, help="frames per device pass (ctx max_batch)")
+    ap.add_argument("--device-batch", type=int, default=16, help="frames per device pass (ctx max_batch); 3 passes are in flight")
     ap.add_argument("--flags", type=int, default=0, help="SIFT_GPU_FLAG_* bits (1 canonical order, 4 FMA blur)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

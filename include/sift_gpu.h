@@ -38,6 +38,7 @@ extern "C" {
 #define SIFT_GPU_FLAG_FMA_BLUR 0x4u        /* fused multiply-add in the Gaussian blur (faster; DoG within 1e-4 relative
                                               of the reference instead of bit-identical to its mulss/addss order) */
 #define SIFT_GPU_FLAG_KEEP_UPSAMPLED 0x8u  /* subpixel: copy the 2x image back (reference overwrites img, sift.cpp:21) */
+#define SIFT_GPU_FLAG_SERIAL 0x10u         /* one device pass at a time (no overlap between passes): clean per-stage timings */
 
 #define SIFT_GPU_DTYPE_F32 0
 #define SIFT_GPU_DTYPE_U8 1

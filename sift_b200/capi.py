@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsift_gpu.so")
 
 OK, E_INVALID, E_CUDA, E_PRECONDITION, E_CAPACITY, E_ASSERT, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-FLAG_ORDER_CANONICAL, FLAG_STRICT, FLAG_FMA_BLUR, FLAG_KEEP_UPSAMPLED = 1, 2, 4, 8
+FLAG_ORDER_CANONICAL, FLAG_STRICT, FLAG_FMA_BLUR, FLAG_KEEP_UPSAMPLED, FLAG_SERIAL = 1, 2, 4, 8, 16
 DTYPE_F32, DTYPE_U8 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 KIND_GAUSS, KIND_DOG = 0, 1

@@ -137,25 +137,32 @@ struct BlurSpec {
 
 static int pitch_of(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
 
+constexpr int kSlots = 3;            // device passes in flight: stage A of pass k+1 overlaps the host replay of pass k and stage B of pass k-1
+constexpr uint32_t kSurvFirst = 8192; // survivors per image copied back speculatively with the counters (the rest on demand)
+
+// The part of a plan that holds device addresses of one slot's buffers.
+struct PlanSlot {
+    CUtensorMap map_up[2], map_base[2], map_chain[kMaxOctaves][kMaxGauss][2], map_reduce[kMaxOctaves][2];  // [0]: 8-row box, [1]: 1-row box
+    bool has_up = false, has_base = false, has_chain[kMaxOctaves][kMaxGauss] = {{false}}, has_reduce[kMaxOctaves] = {false};
+    std::vector<ScanLayer> layers_host;
+    ScanLayer* layers_dev = nullptr;
+    std::vector<LevelRef> targets_host;
+    LevelRef* targets_dev = nullptr;
+};
+
 struct Plan {
     int in_w = 0, in_h = 0, in_pitch = 0;
     int ow[kMaxOctaves] = {0}, oh[kMaxOctaves] = {0}, pitch[kMaxOctaves] = {0};
-    // TMA descriptors of the blur sources (valid[] says whether the streaming kernel can be used)
-    CUtensorMap map_up[2], map_base[2], map_chain[kMaxOctaves][kMaxGauss][2], map_reduce[kMaxOctaves][2];  // [0]: 8-row box, [1]: 1-row box
-    bool has_up = false, has_base = false, has_chain[kMaxOctaves][kMaxGauss] = {{false}}, has_reduce[kMaxOctaves] = {false};
-    size_t sel_x[kMaxOctaves] = {0}, sel_y[kMaxOctaves] = {0};  // decimation: inverse index maps (offsets into d_maps)
     int status = SIFT_GPU_OK;
     std::string why;
     int* d_maps = nullptr;  // all index maps, one allocation
     size_t up_mx = 0, up_my = 0;
-    std::vector<ScanLayer> layers_host;
-    ScanLayer* layers_dev = nullptr;
+    size_t sel_x[kMaxOctaves] = {0}, sel_y[kMaxOctaves] = {0};  // decimation: inverse index maps (offsets into d_maps)
     int total_cols = 0;
     uint32_t mask_words = 0;
-    std::vector<LevelRef> targets_host;
-    LevelRef* targets_dev = nullptr;
     std::vector<int> class_target;  // (octave*dpe + index) -> target slot
-    std::vector<int> target_octave;
+    std::vector<int> target_w, target_h;
+    PlanSlot ps[kSlots];
 };
 
 }  // namespace siftgpu
@@ -164,14 +171,65 @@ using namespace siftgpu;
 
 struct HostImageOut {
     std::vector<sift_gpu_keypoint> kps;
-    std::vector<uint32_t> key_of;  // for each kp: index into the device key list of its chunk, or ~0u
+};
+
+struct ReplayOut {
+    int status = SIFT_GPU_OK;
+    uint32_t n_survivors = 0;
+    std::vector<sift_gpu_keypoint> kps;  // final vector order (orientation/descriptor filled later)
+    std::vector<KeyIn> keys;             // the subset that goes to the device, same order
+    std::vector<uint32_t> key_of;        // kp -> index in keys or ~0u
+};
+
+struct ChunkImage {
+    int result_index;
+    const sift_gpu_image* img;
+};
+
+// One device pass in flight.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[12]{};
+    // device buffers
+    uint8_t* d_in_u8 = nullptr;
+    float* d_in = nullptr;
+    float* d_up_tmp = nullptr;  // blur(img, 1.0) at input resolution
+    float* d_up = nullptr;      // 2x image
+    float* d_gauss[kMaxOctaves][kMaxGauss]{};
+    float* d_dog[kMaxOctaves][kMaxGauss]{};
+    uint32_t* d_mask = nullptr;
+    uint32_t *d_col_count = nullptr, *d_col_off = nullptr;
+    Cand* d_cands = nullptr;
+    Surv* d_surv = nullptr;
+    uint32_t *d_n_cand = nullptr, *d_n_surv = nullptr;
+    uint32_t *h_n_cand = nullptr, *h_n_surv = nullptr;  // pinned
+    Surv* h_surv = nullptr;                              // pinned: B x kSurvFirst (speculative copy)
+    std::vector<std::vector<Surv>> surv_overflow;        // per image, only when n_surv > kSurvFirst
+    // keypoint stage buffers (grow on demand)
+    size_t key_cap = 0;
+    KeyIn* d_keys = nullptr; KeyIn* h_keys = nullptr;
+    uint32_t* d_key_img = nullptr; uint32_t* h_key_img = nullptr;
+    uint32_t* d_key_first = nullptr; uint32_t* h_key_first = nullptr;
+    float* d_orient = nullptr; float* h_orient = nullptr;
+    uint32_t* d_npeaks = nullptr; uint32_t* h_npeaks = nullptr;
+    float* d_peaks = nullptr;
+    float* d_desc = nullptr;
+    float* d_tables = nullptr;
+    size_t tables_cap = 0;
+    // state of the pass in flight
+    Plan* plan = nullptr;
+    std::vector<ChunkImage> imgs;
+    std::vector<ReplayOut> rep;
+    size_t n_keys = 0;
+    float* h_desc = nullptr;
+    uint64_t launches = 0;
+    bool busy = false;
 };
 
 struct sift_gpu_ctx {
     sift_gpu_params prm{};
     int O = 0, D = 0, G = 0;
     bool fma = false;
-    cudaStream_t stream = nullptr;
     std::string error;
 
     // schedule (size independent)
@@ -186,40 +244,14 @@ struct sift_gpu_ctx {
 
     // sizing
     int B = 1;
+    int n_slots = 1;
     int max_in_w = 0, max_in_h = 0, max_in_pitch = 0;
     size_t max_in_px = 0;       // per-image stride of the input staging buffers (pitched)
     size_t maxP[kMaxOctaves]{};
-    size_t cand_cap = 0;
+    size_t cand_cap = 0, mask_cap = 0, col_cap = 0;
 
-    // device buffers
-    uint8_t* d_in_u8 = nullptr;
-    float* d_in = nullptr;
-    float* d_up_tmp = nullptr;  // blur(img, 1.0) at input resolution
-    float* d_up = nullptr;      // 2x image
-    float* d_gauss[kMaxOctaves][kMaxGauss]{};
-    float* d_dog[kMaxOctaves][kMaxGauss]{};
-    uint32_t* d_mask = nullptr;
-    size_t mask_cap = 0;
-    uint32_t *d_col_count = nullptr, *d_col_off = nullptr;
-    size_t col_cap = 0;
-    Cand* d_cands = nullptr;
-    Surv* d_surv = nullptr;
-    uint32_t *d_n_cand = nullptr, *d_n_surv = nullptr;
-    uint32_t *h_n_cand = nullptr, *h_n_surv = nullptr;  // pinned
-    Surv* h_surv = nullptr;                              // pinned, grows
-    size_t h_surv_cap = 0;
-
-    // keypoint stage buffers (grow on demand)
-    size_t key_cap = 0;
-    KeyIn* d_keys = nullptr; KeyIn* h_keys = nullptr;
-    uint32_t* d_key_img = nullptr; uint32_t* h_key_img = nullptr;
-    uint32_t* d_key_first = nullptr; uint32_t* h_key_first = nullptr;
-    float* d_orient = nullptr; float* h_orient = nullptr;
-    uint32_t* d_npeaks = nullptr; uint32_t* h_npeaks = nullptr;
-    float* d_peaks = nullptr;
-    float* d_desc = nullptr;
-    float* d_tables = nullptr;
-    size_t tables_cap = 0;
+    Slot slots[kSlots];
+    int last_slot = -1;  // slot of the most recent pass (stage-level getters read it)
 
     // per-run result storage (pinned descriptor blocks + host vectors)
     std::vector<float*> desc_blocks;
@@ -228,12 +260,10 @@ struct sift_gpu_ctx {
     std::vector<HostImageOut> outs;
 
     std::map<std::pair<int, int>, Plan*> plans;
-    Plan* last_plan = nullptr;
-    int last_batch = 0;
     Pool* pool = nullptr;
 
     sift_gpu_timings tm{};
-    cudaEvent_t ev[12]{};
+    cudaEvent_t ev_first = nullptr, ev_last = nullptr;
 };
 
 static int set_error(sift_gpu_ctx* c, int code, const std::string& msg) {
@@ -359,7 +389,6 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
         maps.insert(maps.end(), m.begin(), m.end());
         return off;
     };
-    if (c->prm.subpixel) { p->up_mx = push_map(in_w, in_w * 2); p->up_my = push_map(in_h, in_h * 2); }
     auto push_inverse = [&](int n_old, int n_new) {  // source index -> destination index, or -1
         size_t off = maps.size();
         std::vector<int> m = resize_index_map(n_old, n_new), inv((size_t)n_old, -1);
@@ -367,6 +396,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
         maps.insert(maps.end(), inv.begin(), inv.end());
         return off;
     };
+    if (c->prm.subpixel) { p->up_mx = push_map(in_w, in_w * 2); p->up_my = push_map(in_h, in_h * 2); }
     for (int o = 0; o + 1 < O; ++o) { p->sel_x[o] = push_inverse(p->ow[o], p->ow[o + 1]); p->sel_y[o] = push_inverse(p->oh[o], p->oh[o + 1]); }
     if (!maps.empty()) {
         if (cudaMalloc(&p->d_maps, sizeof(int) * maps.size()) != cudaSuccess ||
@@ -375,62 +405,70 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
             return p;
         }
     }
-    // extrema scan layers, ordered (octave, index)
-    uint32_t mask_off = 0, col_base = 0;
-    for (int e = 0; e < O; ++e)
-        for (int i = 1; i < D - 1; ++i) {
-            ScanLayer L{};
-            L.d0 = c->d_dog[e][i - 1]; L.d1 = c->d_dog[e][i]; L.d2 = c->d_dog[e][i + 1];
-            L.stride = c->maxP[e];
-            L.pitch = p->pitch[e];
-            L.w = p->ow[e]; L.h = p->oh[e];
-            L.n_yw = (L.h + 31) / 32;
-            L.mask_off = mask_off; L.col_base = col_base;
-            L.octave = (uint8_t)e; L.index = (uint8_t)i;
-            mask_off += (uint32_t)L.n_yw * (uint32_t)L.w;
-            col_base += (uint32_t)L.w;
-            p->layers_host.push_back(L);
-        }
-    p->mask_words = mask_off;
-    p->total_cols = (int)col_base;
-    // nearest-Gaussian targets per keypoint class
+    // nearest-Gaussian targets per keypoint class (identical for every slot; only the base pointers differ)
     p->class_target.assign((size_t)(O * D), -1);
+    std::vector<std::pair<int, int>> target_level;
     for (int e = 0; e < O; ++e)
         for (int i = 1; i < D - 1; ++i) {
             int to, ti;
             nearest_gaussian(c, c->d_scale[e][i], &to, &ti);
             int slot = -1;
-            for (size_t s = 0; s < p->targets_host.size(); ++s)
-                if (p->targets_host[s].base == c->d_gauss[to][ti]) slot = (int)s;
+            for (size_t s = 0; s < target_level.size(); ++s)
+                if (target_level[s] == std::make_pair(to, ti)) slot = (int)s;
             if (slot < 0) {
-                slot = (int)p->targets_host.size();
-                p->targets_host.push_back(LevelRef{c->d_gauss[to][ti], c->maxP[to], p->pitch[to], p->ow[to], p->oh[to]});
-                p->target_octave.push_back(to);
+                slot = (int)target_level.size();
+                target_level.push_back(std::make_pair(to, ti));
+                p->target_w.push_back(p->ow[to]);
+                p->target_h.push_back(p->oh[to]);
             }
             p->class_target[(size_t)(e * D + i)] = slot;
         }
-    if (cudaMalloc(&p->layers_dev, sizeof(ScanLayer) * p->layers_host.size()) != cudaSuccess ||
-        cudaMemcpy(p->layers_dev, p->layers_host.data(), sizeof(ScanLayer) * p->layers_host.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMalloc(&p->targets_dev, sizeof(LevelRef) * p->targets_host.size()) != cudaSuccess ||
-        cudaMemcpy(p->targets_dev, p->targets_host.data(), sizeof(LevelRef) * p->targets_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
-        fail(SIFT_GPU_E_CUDA, "plan upload failed");
-    // TMA descriptors (box width depends on the blur radius); a missing descriptor only means the generic kernel runs
-    auto mk = [&](CUtensorMap* m, const float* base, int w, int h, int pitch, size_t stride, int r) {
-        const int bw = stream_box_width(r);
-        return bw > 0 && tma::make_image_map(&m[0], base, w, h, c->B, (size_t)pitch, stride, bw, 8) &&
-               tma::make_image_map(&m[1], base, w, h, c->B, (size_t)pitch, stride, bw, 1);
-    };
-    if (c->prm.subpixel) {
-        p->has_up = mk(p->map_up, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->up_blur.r);
-        p->has_base = mk(p->map_base, c->d_up, p->ow[0], p->oh[0], p->pitch[0], c->maxP[0], c->base_blur.r);
-    } else {
-        p->has_base = mk(p->map_base, c->d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->base_blur.r);
-    }
-    for (int o = 0; o < O; ++o) {
-        for (int j = 1; j <= D; ++j)
-            p->has_chain[o][j] = mk(p->map_chain[o][j], c->d_gauss[o][j - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->chain_blur[o][j].r);
-        if (o < O - 1)
-            p->has_reduce[o] = mk(p->map_reduce[o], c->d_gauss[o][D - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->reduce_blur[o].r);
+    for (int si = 0; si < c->n_slots; ++si) {
+        Slot& S = c->slots[si];
+        PlanSlot& ps = p->ps[si];
+        // extrema scan layers, ordered (octave, index)
+        uint32_t mask_off = 0, col_base = 0;
+        for (int e = 0; e < O; ++e)
+            for (int i = 1; i < D - 1; ++i) {
+                ScanLayer L{};
+                L.d0 = S.d_dog[e][i - 1]; L.d1 = S.d_dog[e][i]; L.d2 = S.d_dog[e][i + 1];
+                L.stride = c->maxP[e];
+                L.pitch = p->pitch[e];
+                L.w = p->ow[e]; L.h = p->oh[e];
+                L.n_yw = (L.h + 31) / 32;
+                L.mask_off = mask_off; L.col_base = col_base;
+                L.octave = (uint8_t)e; L.index = (uint8_t)i;
+                mask_off += (uint32_t)L.n_yw * (uint32_t)L.w;
+                col_base += (uint32_t)L.w;
+                ps.layers_host.push_back(L);
+            }
+        p->mask_words = mask_off;
+        p->total_cols = (int)col_base;
+        for (auto& tl : target_level)
+            ps.targets_host.push_back(LevelRef{S.d_gauss[tl.first][tl.second], c->maxP[tl.first], p->pitch[tl.first], p->ow[tl.first], p->oh[tl.first]});
+        if (cudaMalloc(&ps.layers_dev, sizeof(ScanLayer) * ps.layers_host.size()) != cudaSuccess ||
+            cudaMemcpy(ps.layers_dev, ps.layers_host.data(), sizeof(ScanLayer) * ps.layers_host.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&ps.targets_dev, sizeof(LevelRef) * ps.targets_host.size()) != cudaSuccess ||
+            cudaMemcpy(ps.targets_dev, ps.targets_host.data(), sizeof(LevelRef) * ps.targets_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            fail(SIFT_GPU_E_CUDA, "plan upload failed");
+        // TMA descriptors (box width depends on the blur radius); a missing descriptor only means the generic kernel runs
+        auto mk = [&](CUtensorMap* m, const float* base, int w, int h, int pitch, size_t stride, int r) {
+            const int bw = stream_box_width(r);
+            return bw > 0 && tma::make_image_map(&m[0], base, w, h, c->B, (size_t)pitch, stride, bw, 8) &&
+                   tma::make_image_map(&m[1], base, w, h, c->B, (size_t)pitch, stride, bw, 1);
+        };
+        if (c->prm.subpixel) {
+            ps.has_up = mk(ps.map_up, S.d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->up_blur.r);
+            ps.has_base = mk(ps.map_base, S.d_up, p->ow[0], p->oh[0], p->pitch[0], c->maxP[0], c->base_blur.r);
+        } else {
+            ps.has_base = mk(ps.map_base, S.d_in, in_w, in_h, p->in_pitch, c->max_in_px, c->base_blur.r);
+        }
+        for (int o = 0; o < O; ++o) {
+            for (int j = 1; j <= D; ++j)
+                ps.has_chain[o][j] = mk(ps.map_chain[o][j], S.d_gauss[o][j - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->chain_blur[o][j].r);
+            if (o < O - 1)
+                ps.has_reduce[o] = mk(ps.map_reduce[o], S.d_gauss[o][D - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->reduce_blur[o].r);
+        }
     }
     return p;
 }
@@ -449,57 +487,56 @@ static int alloc_buffers(sift_gpu_ctx* c) {
         col_cap += (size_t)ow[o] * (size_t)(D - 2);
     }
     c->cand_cap = cand_cap; c->mask_cap = mask_cap; c->col_cap = col_cap;
-    CTX_CUDA(cudaMalloc(&c->d_in_u8, c->max_in_px * (size_t)B));
-    CTX_CUDA(cudaMalloc(&c->d_in, sizeof(float) * c->max_in_px * (size_t)B));
-    if (c->prm.subpixel) {
-        CTX_CUDA(cudaMalloc(&c->d_up_tmp, sizeof(float) * c->max_in_px * (size_t)B));
-        CTX_CUDA(cudaMalloc(&c->d_up, sizeof(float) * c->maxP[0] * (size_t)B));
+    for (int si = 0; si < c->n_slots; ++si) {
+        Slot& S = c->slots[si];
+        CTX_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+        for (auto& e : S.ev) CTX_CUDA(cudaEventCreate(&e));
+        CTX_CUDA(cudaMalloc(&S.d_in_u8, c->max_in_px * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_in, sizeof(float) * c->max_in_px * (size_t)B));
+        if (c->prm.subpixel) {
+            CTX_CUDA(cudaMalloc(&S.d_up_tmp, sizeof(float) * c->max_in_px * (size_t)B));
+            CTX_CUDA(cudaMalloc(&S.d_up, sizeof(float) * c->maxP[0] * (size_t)B));
+        }
+        for (int o = 0; o < O; ++o) {
+            for (int i = 0; i <= D; ++i) CTX_CUDA(cudaMalloc(&S.d_gauss[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
+            for (int i = 0; i < D; ++i) CTX_CUDA(cudaMalloc(&S.d_dog[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
+        }
+        CTX_CUDA(cudaMalloc(&S.d_mask, sizeof(uint32_t) * mask_cap * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_col_count, sizeof(uint32_t) * col_cap * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_col_off, sizeof(uint32_t) * col_cap * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_cands, sizeof(Cand) * cand_cap * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_surv, sizeof(Surv) * cand_cap * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_n_cand, sizeof(uint32_t) * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_n_surv, sizeof(uint32_t) * (size_t)B));
+        CTX_CUDA(cudaHostAlloc(&S.h_n_cand, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
+        CTX_CUDA(cudaHostAlloc(&S.h_n_surv, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
+        CTX_CUDA(cudaHostAlloc(&S.h_surv, sizeof(Surv) * (size_t)kSurvFirst * (size_t)B, cudaHostAllocDefault));
+        CTX_CUDA(cudaMalloc(&S.d_key_first, sizeof(uint32_t) * (size_t)(B + 1)));
+        CTX_CUDA(cudaHostAlloc(&S.h_key_first, sizeof(uint32_t) * (size_t)(B + 1), cudaHostAllocDefault));
+        S.surv_overflow.resize((size_t)B);
     }
-    for (int o = 0; o < O; ++o) {
-        for (int i = 0; i <= D; ++i) CTX_CUDA(cudaMalloc(&c->d_gauss[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
-        for (int i = 0; i < D; ++i) CTX_CUDA(cudaMalloc(&c->d_dog[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
-    }
-    CTX_CUDA(cudaMalloc(&c->d_mask, sizeof(uint32_t) * mask_cap * (size_t)B));
-    CTX_CUDA(cudaMalloc(&c->d_col_count, sizeof(uint32_t) * col_cap * (size_t)B));
-    CTX_CUDA(cudaMalloc(&c->d_col_off, sizeof(uint32_t) * col_cap * (size_t)B));
-    CTX_CUDA(cudaMalloc(&c->d_cands, sizeof(Cand) * cand_cap * (size_t)B));
-    CTX_CUDA(cudaMalloc(&c->d_surv, sizeof(Surv) * cand_cap * (size_t)B));
-    CTX_CUDA(cudaMalloc(&c->d_n_cand, sizeof(uint32_t) * (size_t)B));
-    CTX_CUDA(cudaMalloc(&c->d_n_surv, sizeof(uint32_t) * (size_t)B));
-    CTX_CUDA(cudaHostAlloc(&c->h_n_cand, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
-    CTX_CUDA(cudaHostAlloc(&c->h_n_surv, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
-    CTX_CUDA(cudaMalloc(&c->d_key_first, sizeof(uint32_t) * (size_t)(B + 1)));
-    CTX_CUDA(cudaHostAlloc(&c->h_key_first, sizeof(uint32_t) * (size_t)(B + 1), cudaHostAllocDefault));
+    CTX_CUDA(cudaEventCreate(&c->ev_first));
+    CTX_CUDA(cudaEventCreate(&c->ev_last));
     return 0;
 }
 
-static int ensure_key_capacity(sift_gpu_ctx* c, size_t n) {
-    if (n <= c->key_cap) return 0;
+static int ensure_key_capacity(sift_gpu_ctx* c, Slot& S, size_t n) {
+    if (n <= S.key_cap) return 0;
     size_t cap = std::max<size_t>(n * 3 / 2, 4096);
-    cudaFree(c->d_keys); cudaFree(c->d_key_img); cudaFree(c->d_orient); cudaFree(c->d_npeaks); cudaFree(c->d_peaks); cudaFree(c->d_desc);
-    cudaFreeHost(c->h_keys); cudaFreeHost(c->h_key_img); cudaFreeHost(c->h_orient); cudaFreeHost(c->h_npeaks);
-    c->key_cap = 0;
-    CTX_CUDA(cudaMalloc(&c->d_keys, sizeof(KeyIn) * cap));
-    CTX_CUDA(cudaMalloc(&c->d_key_img, sizeof(uint32_t) * cap));
-    CTX_CUDA(cudaMalloc(&c->d_orient, sizeof(float) * cap));
-    CTX_CUDA(cudaMalloc(&c->d_npeaks, sizeof(uint32_t) * cap));
-    CTX_CUDA(cudaMalloc(&c->d_peaks, sizeof(float) * 36 * cap));
-    CTX_CUDA(cudaMalloc(&c->d_desc, sizeof(float) * kDescLen * cap));
-    CTX_CUDA(cudaHostAlloc(&c->h_keys, sizeof(KeyIn) * cap, cudaHostAllocDefault));
-    CTX_CUDA(cudaHostAlloc(&c->h_key_img, sizeof(uint32_t) * cap, cudaHostAllocDefault));
-    CTX_CUDA(cudaHostAlloc(&c->h_orient, sizeof(float) * cap, cudaHostAllocDefault));
-    CTX_CUDA(cudaHostAlloc(&c->h_npeaks, sizeof(uint32_t) * cap, cudaHostAllocDefault));
-    c->key_cap = cap;
-    return 0;
-}
-
-static int ensure_surv_capacity(sift_gpu_ctx* c, size_t n) {
-    if (n <= c->h_surv_cap) return 0;
-    size_t cap = std::max<size_t>(n * 3 / 2, 1 << 16);
-    cudaFreeHost(c->h_surv);
-    c->h_surv_cap = 0;
-    CTX_CUDA(cudaHostAlloc(&c->h_surv, sizeof(Surv) * cap, cudaHostAllocDefault));
-    c->h_surv_cap = cap;
+    cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_orient); cudaFree(S.d_npeaks); cudaFree(S.d_peaks); cudaFree(S.d_desc);
+    cudaFreeHost(S.h_keys); cudaFreeHost(S.h_key_img); cudaFreeHost(S.h_orient); cudaFreeHost(S.h_npeaks);
+    S.key_cap = 0;
+    CTX_CUDA(cudaMalloc(&S.d_keys, sizeof(KeyIn) * cap));
+    CTX_CUDA(cudaMalloc(&S.d_key_img, sizeof(uint32_t) * cap));
+    CTX_CUDA(cudaMalloc(&S.d_orient, sizeof(float) * cap));
+    CTX_CUDA(cudaMalloc(&S.d_npeaks, sizeof(uint32_t) * cap));
+    CTX_CUDA(cudaMalloc(&S.d_peaks, sizeof(float) * 36 * cap));
+    CTX_CUDA(cudaMalloc(&S.d_desc, sizeof(float) * kDescLen * cap));
+    CTX_CUDA(cudaHostAlloc(&S.h_keys, sizeof(KeyIn) * cap, cudaHostAllocDefault));
+    CTX_CUDA(cudaHostAlloc(&S.h_key_img, sizeof(uint32_t) * cap, cudaHostAllocDefault));
+    CTX_CUDA(cudaHostAlloc(&S.h_orient, sizeof(float) * cap, cudaHostAllocDefault));
+    CTX_CUDA(cudaHostAlloc(&S.h_npeaks, sizeof(uint32_t) * cap, cudaHostAllocDefault));
+    S.key_cap = cap;
     return 0;
 }
 
@@ -527,47 +564,45 @@ static float* take_desc_block(sift_gpu_ctx* c, size_t floats) {
 }
 
 // ---- device passes ------------------------------------------------------------------------------
-static BlurArgs blur_args(const sift_gpu_ctx* c, const std::vector<float>& host_taps, const BlurSpec& b, const float* src,
-                          size_t sstride, int spitch, float* dst, size_t dstride, int dpitch, float* dog, size_t gstride, int gpitch,
-                          int w, int h, const CUtensorMap* map) {
+static BlurArgs blur_args(const sift_gpu_ctx* c, const BlurSpec& b, const float* src, size_t sstride, int spitch, float* dst, size_t dstride,
+                          int dpitch, float* dog, size_t gstride, int gpitch, int w, int h, const CUtensorMap* map) {
     BlurArgs a{};
     a.src = src; a.dst = dst; a.dog = dog;
     a.src_stride = sstride; a.dst_stride = dstride; a.dog_stride = gstride;
     a.src_pitch = spitch; a.dst_pitch = dpitch; a.dog_pitch = gpitch;
-    a.w = w; a.h = h; a.taps = c->d_taps + b.tap_off; a.taps_host = host_taps.data() + b.tap_off; a.r = b.r;
+    a.w = w; a.h = h; a.taps = c->d_taps + b.tap_off; a.taps_host = c->h_taps.data() + b.tap_off; a.r = b.r;
     a.map = map;
     return a;
 }
 
-// Sift::calculate's upsample (sift.cpp:20-21) + _createDOGs (sift.cpp:381-417) for nb images in d_in.
-static int run_pyramid(sift_gpu_ctx* c, const Plan* p, int nb) {
+// Sift::calculate's upsample (sift.cpp:20-21) + _createDOGs (sift.cpp:381-417) for nb images in S.d_in.
+static int run_pyramid(sift_gpu_ctx* c, Slot& S, const Plan* p, const PlanSlot& ps, int nb) {
     const int O = c->O, D = c->D;
-    uint64_t* L = &c->tm.kernel_launches;
-    cudaStream_t s = c->stream;
-    const std::vector<float>& ht = c->h_taps;
-    const float* base_src = c->d_in;
+    uint64_t* L = &S.launches;
+    cudaStream_t s = S.stream;
+    const float* base_src = S.d_in;
     size_t base_stride = c->max_in_px;
     int base_pitch = p->in_pitch;
     if (c->prm.subpixel) {
-        CTX_TRY(launch_blur(blur_args(c, ht, c->up_blur, c->d_in, c->max_in_px, p->in_pitch, c->d_up_tmp, c->max_in_px, p->in_pitch, nullptr, 0, 0,
-                                      p->in_w, p->in_h, p->has_up ? p->map_up : nullptr), nb, c->fma, s, L));
-        CTX_TRY(launch_resize_nn(c->d_up_tmp, c->max_in_px, p->in_pitch, c->d_up, c->maxP[0], p->pitch[0], p->ow[0], p->oh[0],
+        CTX_TRY(launch_blur(blur_args(c, c->up_blur, S.d_in, c->max_in_px, p->in_pitch, S.d_up_tmp, c->max_in_px, p->in_pitch, nullptr, 0, 0,
+                                      p->in_w, p->in_h, ps.has_up ? ps.map_up : nullptr), nb, c->fma, s, L));
+        CTX_TRY(launch_resize_nn(S.d_up_tmp, c->max_in_px, p->in_pitch, S.d_up, c->maxP[0], p->pitch[0], p->ow[0], p->oh[0],
                                  p->d_maps + p->up_mx, p->d_maps + p->up_my, nb, s, L));
-        base_src = c->d_up;
+        base_src = S.d_up;
         base_stride = c->maxP[0];
         base_pitch = p->pitch[0];
     }
-    CTX_TRY(launch_blur(blur_args(c, ht, c->base_blur, base_src, base_stride, base_pitch, c->d_gauss[0][0], c->maxP[0], p->pitch[0], nullptr, 0, 0,
-                                  p->ow[0], p->oh[0], p->has_base ? p->map_base : nullptr), nb, c->fma, s, L));
+    CTX_TRY(launch_blur(blur_args(c, c->base_blur, base_src, base_stride, base_pitch, S.d_gauss[0][0], c->maxP[0], p->pitch[0], nullptr, 0, 0,
+                                  p->ow[0], p->oh[0], ps.has_base ? ps.map_base : nullptr), nb, c->fma, s, L));
     for (int o = 0; o < O; ++o) {
         for (int j = 1; j <= D; ++j)
-            CTX_TRY(launch_blur(blur_args(c, ht, c->chain_blur[o][j], c->d_gauss[o][j - 1], c->maxP[o], p->pitch[o], c->d_gauss[o][j], c->maxP[o],
-                                          p->pitch[o], c->d_dog[o][j - 1], c->maxP[o], p->pitch[o], p->ow[o], p->oh[o],
-                                          p->has_chain[o][j] ? p->map_chain[o][j] : nullptr), nb, c->fma, s, L));
+            CTX_TRY(launch_blur(blur_args(c, c->chain_blur[o][j], S.d_gauss[o][j - 1], c->maxP[o], p->pitch[o], S.d_gauss[o][j], c->maxP[o],
+                                          p->pitch[o], S.d_dog[o][j - 1], c->maxP[o], p->pitch[o], p->ow[o], p->oh[o],
+                                          ps.has_chain[o][j] ? ps.map_chain[o][j] : nullptr), nb, c->fma, s, L));
         if (o < O - 1) {
             // alg::reduceToNextLevel: blur with the level's own label sigma, keep only the pixels the resize picks
-            BlurArgs a = blur_args(c, ht, c->reduce_blur[o], c->d_gauss[o][D - 1], c->maxP[o], p->pitch[o], c->d_gauss[o + 1][0], c->maxP[o + 1],
-                                   p->pitch[o + 1], nullptr, 0, 0, p->ow[o], p->oh[o], p->has_reduce[o] ? p->map_reduce[o] : nullptr);
+            BlurArgs a = blur_args(c, c->reduce_blur[o], S.d_gauss[o][D - 1], c->maxP[o], p->pitch[o], S.d_gauss[o + 1][0], c->maxP[o + 1],
+                                   p->pitch[o + 1], nullptr, 0, 0, p->ow[o], p->oh[o], ps.has_reduce[o] ? ps.map_reduce[o] : nullptr);
             a.sel_x = p->d_maps + p->sel_x[o];
             a.sel_y = p->d_maps + p->sel_y[o];
             CTX_TRY(launch_blur(a, nb, c->fma, s, L));
@@ -593,14 +628,6 @@ static void cleanup_order(const std::vector<uint8_t>& flags, bool canonical, std
     for (size_t i = 0; i < size; ++i) (*kept)[i] = v[i] & 0x7fffffffu;
 }
 
-struct ReplayOut {
-    int status = SIFT_GPU_OK;
-    uint32_t n_survivors = 0;
-    std::vector<sift_gpu_keypoint> kps;  // final vector order (orientation/descriptor filled later)
-    std::vector<KeyIn> keys;             // the subset that goes to the device, same order
-    std::vector<uint32_t> key_of;        // kp -> index in keys or ~0u
-};
-
 // Host half of Sift::calculate between _eliminateEdgeResponses and _createDecriptors (sift.cpp:37-55).
 static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, const Surv* surv_in, uint32_t n_surv,
                          ReplayOut* out) {
@@ -625,8 +652,9 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
     std::vector<uint8_t> flags2(L1.size());
     for (size_t i = 0; i < L1.size(); ++i) {
         const Surv& s = S[L1[i]];
-        const LevelRef& T = p->targets_host[(size_t)p->class_target[(size_t)(s.octave * D + s.index)]];
-        const bool outside = (s.x < kRegion || s.x >= T.w - kRegion) || (s.y < kRegion || s.y >= T.h - kRegion);
+        const int slot = p->class_target[(size_t)(s.octave * D + s.index)];
+        const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
+        const bool outside = (s.x < kRegion || s.x >= tw - kRegion) || (s.y < kRegion || s.y >= th - kRegion);
         flags2[i] = outside ? 1 : 0;
         if (!outside && (c->prm.flags & SIFT_GPU_FLAG_STRICT) && 2 * kRegion < c->dead_blur_r[s.octave][s.index] + 1) {
             out->status = SIFT_GPU_E_PRECONDITION;
@@ -641,14 +669,14 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
     for (size_t i = 0; i < L2.size(); ++i) {
         const Surv& s = S[L1[L2[i]]];
         const int slot = p->class_target[(size_t)(s.octave * D + s.index)];
-        const LevelRef& T = p->targets_host[(size_t)slot];
+        const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
         sift_gpu_keypoint& k = out->kps[i];
         k.x = s.x; k.y = s.y; k.octave = s.octave; k.index = s.index;
         k.scale = c->d_scale[s.octave][s.index];
         k.orientation = 0.0f;
         k.reserved = 0;
         // _createDecriptors bounds test (sift.cpp:65-70)
-        const bool reject = s.x < kRegion || s.x > T.w - kRegion || s.y < kRegion || s.y > T.h - kRegion;
+        const bool reject = s.x < kRegion || s.x > tw - kRegion || s.y < kRegion || s.y > th - kRegion;
         k.filtered = reject ? 1 : 0;
         k.desc_len = reject ? 0 : kDescLen;
         if (!reject) {
@@ -660,162 +688,179 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
     }
 }
 
-struct ChunkImage {
-    int result_index;
-    const sift_gpu_image* img;
-};
-
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static int run_chunk(sift_gpu_ctx* c, Plan* p, const std::vector<ChunkImage>& imgs, sift_gpu_result* results) {
-    const int nb = (int)imgs.size();
-    cudaStream_t s = c->stream;
-    uint64_t* L = &c->tm.kernel_launches;
-    c->last_plan = p;
-    c->last_batch = nb;
-
-    CTX_CUDA(cudaEventRecord(c->ev[0], s));
+// Stage A: upload, pyramid, extrema, elimination, counters + first survivors back.  Asynchronous.
+static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
+    Plan* p = S.plan;
+    const PlanSlot& ps = p->ps[slot_index];
+    const int nb = (int)S.imgs.size();
+    cudaStream_t s = S.stream;
+    uint64_t* L = &S.launches;
+    S.launches = 0;
+    CTX_CUDA(cudaEventRecord(S.ev[0], s));
     // upload (main.cpp:52-54 leaves band 0 as float 0..255; u8 input is widened on the device)
     for (int b = 0; b < nb; ++b) {
-        const sift_gpu_image& im = *imgs[(size_t)b].img;
+        const sift_gpu_image& im = *S.imgs[(size_t)b].img;
         const size_t esz = im.dtype == SIFT_GPU_DTYPE_U8 ? 1 : 4;
         const size_t pitch = im.row_stride_bytes ? (size_t)im.row_stride_bytes : (size_t)im.width * esz;
-        void* dst = im.dtype == SIFT_GPU_DTYPE_U8 ? (void*)(c->d_in_u8 + (size_t)b * c->max_in_px)
-                                                  : (void*)(c->d_in + (size_t)b * c->max_in_px);
+        void* dst = im.dtype == SIFT_GPU_DTYPE_U8 ? (void*)(S.d_in_u8 + (size_t)b * c->max_in_px) : (void*)(S.d_in + (size_t)b * c->max_in_px);
         const cudaMemcpyKind kind = im.memory == SIFT_GPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->in_pitch * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
     }
-    if (imgs[0].img->dtype == SIFT_GPU_DTYPE_U8)
-        CTX_TRY(launch_u8_to_f32(c->d_in_u8, c->max_in_px, p->in_pitch, c->d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, nb, s, L));
-    CTX_CUDA(cudaEventRecord(c->ev[1], s));
-    CTX_TRY(run_pyramid(c, p, nb));
-    CTX_CUDA(cudaEventRecord(c->ev[2], s));
-    CTX_TRY(launch_extrema(p->layers_dev, p->layers_host.data(), (int)p->layers_host.size(), p->total_cols, p->mask_words,
-                           c->d_mask, c->d_col_count, c->d_col_off, c->d_cands, c->cand_cap, c->d_n_cand, nb, s, L));
-    CTX_CUDA(cudaEventRecord(c->ev[3], s));
-    CTX_TRY(launch_eliminate(p->layers_dev, (int)p->layers_host.size(), c->d_cands, c->cand_cap, c->d_n_cand, c->d_surv,
-                             c->cand_cap, c->d_n_surv, c->D, nb, s, L));
-    CTX_CUDA(cudaEventRecord(c->ev[4], s));
-    CTX_CUDA(cudaMemcpyAsync(c->h_n_cand, c->d_n_cand, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(cudaMemcpyAsync(c->h_n_surv, c->d_n_surv, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(cudaStreamSynchronize(s));
-    std::vector<size_t> surv_off((size_t)nb + 1, 0);
-    for (int b = 0; b < nb; ++b) surv_off[(size_t)b + 1] = surv_off[(size_t)b] + c->h_n_surv[b];
-    CTX_TRY(ensure_surv_capacity(c, surv_off[(size_t)nb]));
-    for (int b = 0; b < nb; ++b)
-        if (c->h_n_surv[b])
-            CTX_CUDA(cudaMemcpyAsync(c->h_surv + surv_off[(size_t)b], c->d_surv + (size_t)b * c->cand_cap,
-                                     sizeof(Surv) * c->h_n_surv[b], cudaMemcpyDeviceToHost, s));
+    if (S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8)
+        CTX_TRY(launch_u8_to_f32(S.d_in_u8, c->max_in_px, p->in_pitch, S.d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, nb, s, L));
+    CTX_CUDA(cudaEventRecord(S.ev[1], s));
+    CTX_TRY(run_pyramid(c, S, p, ps, nb));
+    CTX_CUDA(cudaEventRecord(S.ev[2], s));
+    CTX_TRY(launch_extrema(ps.layers_dev, ps.layers_host.data(), (int)ps.layers_host.size(), p->total_cols, p->mask_words, S.d_mask,
+                           S.d_col_count, S.d_col_off, S.d_cands, c->cand_cap, S.d_n_cand, nb, s, L));
+    CTX_CUDA(cudaEventRecord(S.ev[3], s));
+    CTX_TRY(launch_eliminate(ps.layers_dev, (int)ps.layers_host.size(), S.d_cands, c->cand_cap, S.d_n_cand, S.d_surv, c->cand_cap,
+                             S.d_n_surv, c->D, nb, s, L));
+    CTX_CUDA(cudaEventRecord(S.ev[4], s));
+    CTX_CUDA(cudaMemcpyAsync(S.h_n_cand, S.d_n_cand, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(cudaMemcpyAsync(S.h_n_surv, S.d_n_surv, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    // speculative: the first kSurvFirst survivors of every image travel with the counters (one strided copy)
+    const size_t first = std::min<size_t>(kSurvFirst, c->cand_cap);
+    CTX_CUDA(cudaMemcpy2DAsync(S.h_surv, sizeof(Surv) * kSurvFirst, S.d_surv, sizeof(Surv) * c->cand_cap, sizeof(Surv) * first, (size_t)nb,
+                               cudaMemcpyDeviceToHost, s));
     if (c->prm.subpixel && (c->prm.flags & SIFT_GPU_FLAG_KEEP_UPSAMPLED))
         for (int b = 0; b < nb; ++b)
-            if (imgs[(size_t)b].img->upsampled_out)
-                CTX_CUDA(cudaMemcpy2DAsync(imgs[(size_t)b].img->upsampled_out, sizeof(float) * (size_t)p->ow[0], c->d_up + (size_t)b * c->maxP[0],
+            if (S.imgs[(size_t)b].img->upsampled_out)
+                CTX_CUDA(cudaMemcpy2DAsync(S.imgs[(size_t)b].img->upsampled_out, sizeof(float) * (size_t)p->ow[0], S.d_up + (size_t)b * c->maxP[0],
                                            sizeof(float) * (size_t)p->pitch[0], sizeof(float) * (size_t)p->ow[0], (size_t)p->oh[0], cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(cudaEventRecord(c->ev[5], s));
+    CTX_CUDA(cudaEventRecord(S.ev[5], s));
+    return 0;
+}
+
+// Host order replay of one pass (blocks on stage A), then stage B: keypoints up, orientation, descriptors, results back.
+static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) {
+    Plan* p = S.plan;
+    const PlanSlot& ps = p->ps[slot_index];
+    const int nb = (int)S.imgs.size();
+    cudaStream_t s = S.stream;
+    uint64_t* L = &S.launches;
+    CTX_CUDA(cudaEventSynchronize(S.ev[5]));
+    // images with more survivors than the speculative copy holds fetch the remainder now (rare)
+    for (int b = 0; b < nb; ++b) {
+        S.surv_overflow[(size_t)b].clear();
+        const uint32_t n = S.h_n_surv[b];
+        if (n > c->cand_cap) return set_error(c, SIFT_GPU_E_CAPACITY, "survivor list overflow");
+        if (n > kSurvFirst) {
+            S.surv_overflow[(size_t)b].resize(n);
+            CTX_CUDA(cudaMemcpyAsync(S.surv_overflow[(size_t)b].data(), S.d_surv + (size_t)b * c->cand_cap, sizeof(Surv) * n, cudaMemcpyDeviceToHost, s));
+        }
+    }
     CTX_CUDA(cudaStreamSynchronize(s));
 
-    // host: order replay (one job per image)
     const double t_host0 = now_ms();
-    std::vector<ReplayOut> rep((size_t)nb);
+    S.rep.assign((size_t)nb, ReplayOut());
     c->pool->parallel_for(nb, [&](int b) {
-        replay_image(c, p, c->h_n_cand[b], c->h_surv + surv_off[(size_t)b], c->h_n_surv[b], &rep[(size_t)b]);
+        const uint32_t n = S.h_n_surv[b];
+        const Surv* sv = n > kSurvFirst ? S.surv_overflow[(size_t)b].data() : S.h_surv + (size_t)b * kSurvFirst;
+        replay_image(c, p, S.h_n_cand[b], sv, n, &S.rep[(size_t)b]);
     });
     size_t n_keys = 0;
     for (int b = 0; b < nb; ++b) {
-        c->h_key_first[b] = (uint32_t)n_keys;
-        if (rep[(size_t)b].status == SIFT_GPU_OK) n_keys += rep[(size_t)b].keys.size();
+        S.h_key_first[b] = (uint32_t)n_keys;
+        if (S.rep[(size_t)b].status == SIFT_GPU_OK) n_keys += S.rep[(size_t)b].keys.size();
     }
-    c->h_key_first[nb] = (uint32_t)n_keys;
-    CTX_TRY(ensure_key_capacity(c, n_keys));
+    S.h_key_first[nb] = (uint32_t)n_keys;
+    S.n_keys = n_keys;
+    CTX_TRY(ensure_key_capacity(c, S, n_keys));
     for (int b = 0; b < nb; ++b) {
-        if (rep[(size_t)b].status != SIFT_GPU_OK) continue;
-        const size_t off = c->h_key_first[b];
-        std::copy(rep[(size_t)b].keys.begin(), rep[(size_t)b].keys.end(), c->h_keys + off);
-        std::fill(c->h_key_img + off, c->h_key_img + off + rep[(size_t)b].keys.size(), (uint32_t)b);
+        if (S.rep[(size_t)b].status != SIFT_GPU_OK) continue;
+        const size_t off = S.h_key_first[b];
+        std::copy(S.rep[(size_t)b].keys.begin(), S.rep[(size_t)b].keys.end(), S.h_keys + off);
+        std::fill(S.h_key_img + off, S.h_key_img + off + S.rep[(size_t)b].keys.size(), (uint32_t)b);
     }
     c->tm.host_order_ms += (float)(now_ms() - t_host0);
 
-    CTX_CUDA(cudaEventRecord(c->ev[6], s));
-    float* h_desc = take_desc_block(c, n_keys * kDescLen);
-    if (!h_desc) return set_error(c, SIFT_GPU_E_CUDA, "pinned descriptor block allocation failed");
+    CTX_CUDA(cudaEventRecord(S.ev[6], s));
+    S.h_desc = take_desc_block(c, n_keys * kDescLen);
+    if (!S.h_desc) return set_error(c, SIFT_GPU_E_CUDA, "pinned descriptor block allocation failed");
     if (n_keys) {
-        CTX_CUDA(cudaMemcpyAsync(c->d_keys, c->h_keys, sizeof(KeyIn) * n_keys, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(cudaMemcpyAsync(c->d_key_img, c->h_key_img, sizeof(uint32_t) * n_keys, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(cudaMemcpyAsync(c->d_key_first, c->h_key_first, sizeof(uint32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(S.d_keys, S.h_keys, sizeof(KeyIn) * n_keys, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(S.d_key_img, S.h_key_img, sizeof(uint32_t) * n_keys, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(S.d_key_first, S.h_key_first, sizeof(uint32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, s));
     }
-    CTX_CUDA(cudaEventRecord(c->ev[7], s));
-    const int n_targets = (int)p->targets_host.size();
+    CTX_CUDA(cudaEventRecord(S.ev[7], s));
+    const int n_targets = (int)ps.targets_host.size();
     if (n_keys) {
         const size_t tables_need = (size_t)nb * (size_t)n_targets * 256;
-        if (tables_need > c->tables_cap) {
-            cudaFree(c->d_tables);
-            c->tables_cap = 0;
-            CTX_CUDA(cudaMalloc(&c->d_tables, sizeof(float) * tables_need));
-            c->tables_cap = tables_need;
+        if (tables_need > S.tables_cap) {
+            cudaFree(S.d_tables);
+            S.tables_cap = 0;
+            CTX_CUDA(cudaMalloc(&S.d_tables, sizeof(float) * tables_need));
+            S.tables_cap = tables_need;
         }
-        CTX_TRY(launch_orientation(p->targets_dev, n_targets, c->d_keys, c->d_key_img, (uint32_t)n_keys, c->d_orient, c->d_npeaks,
-                                   c->d_peaks, s, L));
+        CTX_TRY(launch_orientation(ps.targets_dev, n_targets, S.d_keys, S.d_key_img, (uint32_t)n_keys, S.d_orient, S.d_npeaks, S.d_peaks, s, L));
     }
-    CTX_CUDA(cudaEventRecord(c->ev[8], s));
+    CTX_CUDA(cudaEventRecord(S.ev[8], s));
     if (n_keys) {
-        CTX_TRY(launch_weight_tables(p->targets_dev, n_targets, c->d_taps + c->w16_blur.tap_off, c->w16_blur.r, c->d_tables, c->fma,
-                                     nb, s, L));
-        CTX_TRY(launch_descriptors(p->targets_dev, n_targets, c->d_tables, c->d_keys, c->d_key_img, c->d_key_first, (uint32_t)n_keys,
-                                   c->d_orient, c->d_desc, s, L));
+        CTX_TRY(launch_weight_tables(ps.targets_dev, n_targets, c->d_taps + c->w16_blur.tap_off, c->w16_blur.r, S.d_tables, c->fma, nb, s, L));
+        CTX_TRY(launch_descriptors(ps.targets_dev, n_targets, S.d_tables, S.d_keys, S.d_key_img, S.d_key_first, (uint32_t)n_keys, S.d_orient,
+                                   S.d_desc, s, L));
     }
-    CTX_CUDA(cudaEventRecord(c->ev[9], s));
+    CTX_CUDA(cudaEventRecord(S.ev[9], s));
     if (n_keys) {
-        CTX_CUDA(cudaMemcpyAsync(c->h_orient, c->d_orient, sizeof(float) * n_keys, cudaMemcpyDeviceToHost, s));
-        CTX_CUDA(cudaMemcpyAsync(c->h_npeaks, c->d_npeaks, sizeof(uint32_t) * n_keys, cudaMemcpyDeviceToHost, s));
-        CTX_CUDA(cudaMemcpyAsync(h_desc, c->d_desc, sizeof(float) * kDescLen * n_keys, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(cudaMemcpyAsync(S.h_orient, S.d_orient, sizeof(float) * n_keys, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(cudaMemcpyAsync(S.h_npeaks, S.d_npeaks, sizeof(uint32_t) * n_keys, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(cudaMemcpyAsync(S.h_desc, S.d_desc, sizeof(float) * kDescLen * n_keys, cudaMemcpyDeviceToHost, s));
     }
-    CTX_CUDA(cudaEventRecord(c->ev[10], s));
-    CTX_CUDA(cudaStreamSynchronize(s));
+    CTX_CUDA(cudaEventRecord(S.ev[10], s));
+    return 0;
+}
 
-    // assemble results
+// Waits for stage B of the pass in `S` and fills the caller's results.
+static int finish_pass(sift_gpu_ctx* c, Slot& S, sift_gpu_result* results) {
+    Plan* p = S.plan;
+    const int nb = (int)S.imgs.size();
+    CTX_CUDA(cudaEventSynchronize(S.ev[10]));
     for (int b = 0; b < nb; ++b) {
-        const int ri = imgs[(size_t)b].result_index;
+        const int ri = S.imgs[(size_t)b].result_index;
         sift_gpu_result& R = results[ri];
         HostImageOut& HO = c->outs[(size_t)ri];
-        ReplayOut& ro = rep[(size_t)b];
-        R.n_candidates = c->h_n_cand[b];
+        ReplayOut& ro = S.rep[(size_t)b];
+        R.n_candidates = S.h_n_cand[b];
         R.n_survivors = ro.n_survivors;
         R.out_width = p->ow[0]; R.out_height = p->oh[0];
         R.status = ro.status;
         R.n = 0; R.kps = nullptr; R.desc = nullptr;
         if (ro.status != SIFT_GPU_OK) continue;
-        const size_t off = c->h_key_first[b];
+        const size_t off = S.h_key_first[b];
         // descriptors are contiguous per image only if every keypoint went to the device (always so in
         // practice, sift.cpp:65 can never reject what sift.cpp:173 accepted); otherwise rows are spread out.
         bool all = true;
         for (size_t i = 0; i < ro.kps.size(); ++i) {
             const uint32_t ko = ro.key_of[i];
             if (ko == ~0u) { all = false; continue; }
-            if (c->h_npeaks[off + ko] > 1) R.status = SIFT_GPU_E_UNSUPPORTED;  // extra orientations (sift.cpp:194-200)
-            ro.kps[i].orientation = c->h_orient[off + ko];
+            if (S.h_npeaks[off + ko] > 1) R.status = SIFT_GPU_E_UNSUPPORTED;  // extra orientations (sift.cpp:194-200)
+            ro.kps[i].orientation = S.h_orient[off + ko];
         }
         HO.kps.swap(ro.kps);
         R.n = (uint32_t)HO.kps.size();
         R.kps = HO.kps.data();
         if (all) {
-            R.desc = h_desc + off * kDescLen;
+            R.desc = S.h_desc + off * kDescLen;
         } else {
             float* blk = take_desc_block(c, HO.kps.size() * kDescLen);
             if (!blk) return set_error(c, SIFT_GPU_E_CUDA, "pinned descriptor block allocation failed");
             for (size_t i = 0; i < HO.kps.size(); ++i) {
                 if (ro.key_of[i] == ~0u) std::memset(blk + i * kDescLen, 0, sizeof(float) * kDescLen);
-                else std::memcpy(blk + i * kDescLen, h_desc + (off + ro.key_of[i]) * kDescLen, sizeof(float) * kDescLen);
+                else std::memcpy(blk + i * kDescLen, S.h_desc + (off + ro.key_of[i]) * kDescLen, sizeof(float) * kDescLen);
             }
             R.desc = blk;
         }
         if (R.status == SIFT_GPU_E_UNSUPPORTED)
             c->error = "a keypoint produced more than one orientation peak (sift.cpp:194-200): not supported yet";
     }
-    // stage times
-    float ms;
-    auto el = [&](int a, int b2) { cudaEventElapsedTime(&ms, c->ev[a], c->ev[b2]); return ms; };
+    // stage times of this pass (device time of each stage; passes overlap, so their sum can exceed span_ms)
+    float ms = 0.0f;
+    auto el = [&](int a, int b2) { cudaEventElapsedTime(&ms, S.ev[a], S.ev[b2]); return ms; };
     c->tm.h2d_ms += el(0, 1);
     c->tm.pyramid_ms += el(1, 2);
     c->tm.extrema_ms += el(2, 3);
@@ -825,14 +870,15 @@ static int run_chunk(sift_gpu_ctx* c, Plan* p, const std::vector<ChunkImage>& im
     c->tm.orientation_ms += el(7, 8);
     c->tm.descriptor_ms += el(8, 9);
     c->tm.d2h_results_ms += el(9, 10);
-    c->tm.span_ms += el(0, 10);
+    c->tm.kernel_launches += S.launches;
+    S.busy = false;
     return 0;
 }
 
 // =================================================================================================
 extern "C" {
 
-const char* sift_gpu_version(void) { return "sift_b200 0.1 (sm_100a)"; }
+const char* sift_gpu_version(void) { return "sift_b200 0.2 (sm_100a)"; }
 
 const char* sift_gpu_last_error(const sift_gpu_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
 
@@ -856,12 +902,12 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
     c->O = params->octaves; c->D = params->dogs_per_epoch; c->G = c->D + 1;
     c->fma = (params->flags & SIFT_GPU_FLAG_FMA_BLUR) != 0;
     c->B = params->max_batch;
+    c->n_slots = (params->flags & SIFT_GPU_FLAG_SERIAL) ? 1 : kSlots;
+    if (const char* e = getenv("SIFT_GPU_SLOTS")) c->n_slots = std::max(1, std::min(kSlots, atoi(e)));
     c->max_in_w = params->max_width; c->max_in_h = params->max_height;
     int rc = 0;
     auto body = [&]() -> int {
         CTX_CUDA(cudaSetDevice(params->device));
-        CTX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        for (auto& e : c->ev) CTX_CUDA(cudaEventCreate(&e));
         CTX_TRY(build_schedule(c));
         CTX_TRY(alloc_buffers(c));
         return 0;
@@ -875,7 +921,7 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
     }
     int nthreads = 0;
     if (const char* e = getenv("SIFT_GPU_HOST_THREADS")) nthreads = atoi(e);
-    if (nthreads <= 0) nthreads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (nthreads <= 0) nthreads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
     c->pool = new Pool(nthreads - 1);
     *out = c;
     return SIFT_GPU_OK;
@@ -884,26 +930,38 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
 void sift_gpu_destroy(sift_gpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->prm.device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (Slot& S : c->slots)
+        if (S.stream) cudaStreamSynchronize(S.stream);
     delete c->pool;
     for (auto& kv : c->plans) {
         Plan* p = kv.second;
-        cudaFree(p->d_maps); cudaFree(p->layers_dev); cudaFree(p->targets_dev);
+        cudaFree(p->d_maps);
+        for (PlanSlot& ps : p->ps) { cudaFree(ps.layers_dev); cudaFree(ps.targets_dev); }
         delete p;
     }
-    cudaFree(c->d_taps); cudaFree(c->d_in_u8); cudaFree(c->d_in); cudaFree(c->d_up_tmp); cudaFree(c->d_up);
-    for (int o = 0; o < kMaxOctaves; ++o)
-        for (int i = 0; i < kMaxGauss; ++i) { cudaFree(c->d_gauss[o][i]); cudaFree(c->d_dog[o][i]); }
-    cudaFree(c->d_mask); cudaFree(c->d_col_count); cudaFree(c->d_col_off); cudaFree(c->d_cands); cudaFree(c->d_surv);
-    cudaFree(c->d_n_cand); cudaFree(c->d_n_surv); cudaFreeHost(c->h_n_cand); cudaFreeHost(c->h_n_surv); cudaFreeHost(c->h_surv);
-    cudaFree(c->d_keys); cudaFree(c->d_key_img); cudaFree(c->d_key_first); cudaFree(c->d_orient); cudaFree(c->d_npeaks);
-    cudaFree(c->d_peaks); cudaFree(c->d_desc); cudaFree(c->d_tables);
-    cudaFreeHost(c->h_keys); cudaFreeHost(c->h_key_img); cudaFreeHost(c->h_key_first); cudaFreeHost(c->h_orient); cudaFreeHost(c->h_npeaks);
+    cudaFree(c->d_taps);
+    for (Slot& S : c->slots) {
+        cudaFree(S.d_in_u8); cudaFree(S.d_in); cudaFree(S.d_up_tmp); cudaFree(S.d_up);
+        for (int o = 0; o < kMaxOctaves; ++o)
+            for (int i = 0; i < kMaxGauss; ++i) { cudaFree(S.d_gauss[o][i]); cudaFree(S.d_dog[o][i]); }
+        cudaFree(S.d_mask); cudaFree(S.d_col_count); cudaFree(S.d_col_off); cudaFree(S.d_cands); cudaFree(S.d_surv);
+        cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv);
+        cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_key_first); cudaFree(S.d_orient); cudaFree(S.d_npeaks);
+        cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_tables);
+        cudaFreeHost(S.h_keys); cudaFreeHost(S.h_key_img); cudaFreeHost(S.h_key_first); cudaFreeHost(S.h_orient); cudaFreeHost(S.h_npeaks);
+        for (auto& e : S.ev) if (e) cudaEventDestroy(e);
+        if (S.stream) cudaStreamDestroy(S.stream);
+    }
     for (float* b : c->desc_blocks) cudaFreeHost(b);
-    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ev_first) cudaEventDestroy(c->ev_first);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
     delete c;
 }
+
+struct PassPlan {
+    Plan* plan;
+    std::vector<ChunkImage> imgs;
+};
 
 int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, sift_gpu_result* results) {
     if (!c || (n_images > 0 && (!images || !results)) || n_images < 0) return set_error(c, SIFT_GPU_E_INVALID, "null argument");
@@ -915,6 +973,8 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
     c->outs.clear();
     c->outs.resize((size_t)n_images);
     int first_error = SIFT_GPU_OK;
+    // split the images into device passes: runs of equal shape and dtype, at most max_batch each
+    std::vector<PassPlan> passes;
     int i = 0;
     while (i < n_images) {
         const sift_gpu_image& im = images[i];
@@ -939,20 +999,49 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
             ++i;
             continue;
         }
-        std::vector<ChunkImage> chunk;
-        while (i < n_images && (int)chunk.size() < c->B && images[i].data && images[i].width == im.width &&
+        PassPlan pp;
+        pp.plan = p;
+        while (i < n_images && (int)pp.imgs.size() < c->B && images[i].data && images[i].width == im.width &&
                images[i].height == im.height && images[i].dtype == im.dtype) {
             std::memset(&results[i], 0, sizeof(sift_gpu_result));
-            chunk.push_back(ChunkImage{i, &images[i]});
+            pp.imgs.push_back(ChunkImage{i, &images[i]});
             ++i;
         }
-        int rc = run_chunk(c, p, chunk, results);
-        if (rc != 0) return rc;
-        for (const ChunkImage& ci : chunk)
-            if (results[ci.result_index].status != SIFT_GPU_OK && !first_error) {
-                first_error = results[ci.result_index].status;
-                if (first_error == SIFT_GPU_E_PRECONDITION) c->error = "separableConvolveX(): kernel longer than line";
-            }
+        passes.push_back(std::move(pp));
+    }
+    // software pipeline over the passes: A(k) is enqueued before the host replays pass k-1, whose stage B then
+    // runs while A(k+1) is being enqueued and pass k-2 is collected
+    const int np = (int)passes.size(), ns = c->n_slots;
+    const int lag_b = ns >= 2 ? 1 : 0, lag_f = ns >= 3 ? 2 : lag_b;
+    for (int k = 0; k < np + lag_f; ++k) {
+        if (k < np) {
+            Slot& S = c->slots[k % ns];
+            S.plan = passes[(size_t)k].plan;
+            S.imgs = passes[(size_t)k].imgs;
+            S.busy = true;
+            if (k == 0) CTX_CUDA(cudaEventRecord(c->ev_first, S.stream));
+            CTX_TRY(enqueue_stage_a(c, S, k % ns));
+        }
+        const int kb = k - lag_b;
+        if (kb >= 0 && kb < np) CTX_TRY(replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
+        const int kf = k - lag_f;
+        if (kf >= 0 && kf < np) {
+            Slot& S = c->slots[kf % ns];
+            if (kf == np - 1) CTX_CUDA(cudaEventRecord(c->ev_last, S.stream));
+            CTX_TRY(finish_pass(c, S, results));
+            c->last_slot = kf % ns;
+            for (const ChunkImage& ci : S.imgs)
+                if (results[ci.result_index].status != SIFT_GPU_OK && !first_error) {
+                    first_error = results[ci.result_index].status;
+                    if (first_error == SIFT_GPU_E_PRECONDITION) c->error = "separableConvolveX(): kernel longer than line";
+                }
+        }
+    }
+    if (np > 0) {
+        float ms = 0.0f;
+        CTX_CUDA(cudaEventSynchronize(c->ev_last));
+        cudaEventElapsedTime(&ms, c->ev_first, c->ev_last);
+        c->tm.span_ms = ms;
     }
     c->tm.device_total_ms = c->tm.h2d_ms + c->tm.pyramid_ms + c->tm.extrema_ms + c->tm.eliminate_ms + c->tm.d2h_survivors_ms +
                             c->tm.h2d_keypoints_ms + c->tm.orientation_ms + c->tm.descriptor_ms + c->tm.d2h_results_ms;
@@ -969,13 +1058,14 @@ int sift_gpu_get_timings(const sift_gpu_ctx* c, sift_gpu_timings* out) {
 // ---- stage-level entry points -------------------------------------------------------------------
 int sift_gpu_debug_get_level(sift_gpu_ctx* c, int image_idx, int octave, int elem, int kind, float* out, int* width,
                              int* height, float* scale) {
-    if (!c || !c->last_plan) return set_error(c, SIFT_GPU_E_INVALID, "no pass has run yet");
-    const Plan* p = c->last_plan;
-    if (image_idx < 0 || image_idx >= c->last_batch || octave < 0 || octave >= c->O || elem < 0 ||
+    if (!c || c->last_slot < 0) return set_error(c, SIFT_GPU_E_INVALID, "no pass has run yet");
+    const Slot& S = c->slots[c->last_slot];
+    const Plan* p = S.plan;
+    if (image_idx < 0 || image_idx >= (int)S.imgs.size() || octave < 0 || octave >= c->O || elem < 0 ||
         elem >= (kind == SIFT_GPU_KIND_DOG ? c->D : c->G))
         return set_error(c, SIFT_GPU_E_INVALID, "level index out of range");
     CTX_CUDA(cudaSetDevice(c->prm.device));
-    const float* src = (kind == SIFT_GPU_KIND_DOG ? c->d_dog[octave][elem] : c->d_gauss[octave][elem]) + (size_t)image_idx * c->maxP[octave];
+    const float* src = (kind == SIFT_GPU_KIND_DOG ? S.d_dog[octave][elem] : S.d_gauss[octave][elem]) + (size_t)image_idx * c->maxP[octave];
     if (width) *width = p->ow[octave];
     if (height) *height = p->oh[octave];
     if (scale) *scale = kind == SIFT_GPU_KIND_DOG ? c->d_scale[octave][elem] : c->g_scale[octave][elem];
@@ -1030,20 +1120,20 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
             cu(cudaMalloc(&d_map, sizeof(int) * inv.size()));
             if (!rc) cu(cudaMemcpy(d_map, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice));
             a.dst = d_out; a.dst_pitch = dp; a.sel_x = d_map; a.sel_y = d_map + w;
-            if (!rc) rc = launch_blur(a, 1, c->fma, c->stream, nullptr);
+            if (!rc) rc = launch_blur(a, 1, c->fma, c->slots[0].stream, nullptr);
         } else {
             a.dst = mode == 0 ? d_out : d_blur; a.dst_pitch = sp;
-            rc = launch_blur(a, 1, c->fma, c->stream, nullptr);
+            rc = launch_blur(a, 1, c->fma, c->slots[0].stream, nullptr);
             if (!rc && mode == 2) {
                 std::vector<int> both = resize_index_map(w, dw), my = resize_index_map(h, dh);
                 both.insert(both.end(), my.begin(), my.end());
                 cu(cudaMalloc(&d_map, sizeof(int) * both.size()));
                 if (!rc) cu(cudaMemcpy(d_map, both.data(), sizeof(int) * both.size(), cudaMemcpyHostToDevice));
-                if (!rc) rc = launch_resize_nn(d_blur, 0, sp, d_out, 0, dp, dw, dh, d_map, d_map + dw, 1, c->stream, nullptr);
+                if (!rc) rc = launch_resize_nn(d_blur, 0, sp, d_out, 0, dp, dw, dh, d_map, d_map + dw, 1, c->slots[0].stream, nullptr);
             }
         }
     }
-    if (!rc) cu(cudaStreamSynchronize(c->stream));
+    if (!rc) cu(cudaStreamSynchronize(c->slots[0].stream));
     if (!rc) cu(cudaMemcpy2D(dst, sizeof(float) * (size_t)dw, d_out, sizeof(float) * (size_t)dp, sizeof(float) * (size_t)dw, (size_t)dh, cudaMemcpyDeviceToHost));
     cudaFree(d_src); cudaFree(d_blur); cudaFree(d_taps); cudaFree(d_out); cudaFree(d_map);
     if (rc) c->error = g_last_error;
@@ -1088,8 +1178,8 @@ int sift_gpu_debug_extrema(sift_gpu_ctx* c, const float* d0, const float* d1, co
     CTX_CUDA(cudaSetDevice(c->prm.device));
     DebugLayers S;
     CTX_TRY(debug_layers_setup(c, S, d0, d1, d2, w, h));
-    CTX_TRY(launch_extrema(S.dev, &S.L, 1, w, (uint32_t)S.L.n_yw * (uint32_t)w, S.mask, S.cc, S.co, S.cands, 0, S.n_cand, 1, c->stream, nullptr));
-    CTX_CUDA(cudaStreamSynchronize(c->stream));
+    CTX_TRY(launch_extrema(S.dev, &S.L, 1, w, (uint32_t)S.L.n_yw * (uint32_t)w, S.mask, S.cc, S.co, S.cands, 0, S.n_cand, 1, c->slots[0].stream, nullptr));
+    CTX_CUDA(cudaStreamSynchronize(c->slots[0].stream));
     uint32_t n = 0;
     CTX_CUDA(cudaMemcpy(&n, S.n_cand, sizeof n, cudaMemcpyDeviceToHost));
     *n_out = n;
@@ -1117,8 +1207,8 @@ int sift_gpu_debug_eliminate(sift_gpu_ctx* c, const float* d0, const float* d1, 
         rc = SIFT_GPU_E_CUDA;
     if (!rc && n && cudaMemcpy(d_c, hc.data(), sizeof(Cand) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
     if (!rc && cudaMemcpy(S.n_cand, &n, sizeof n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
-    if (!rc) rc = launch_eliminate(S.dev, 1, d_c, 0, S.n_cand, d_s, std::max<uint32_t>(n, 1), d_ns, 3, 1, c->stream, nullptr);
-    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
+    if (!rc) rc = launch_eliminate(S.dev, 1, d_c, 0, S.n_cand, d_s, std::max<uint32_t>(n, 1), d_ns, 3, 1, c->slots[0].stream, nullptr);
+    if (!rc && cudaStreamSynchronize(c->slots[0].stream) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
     if (!rc && n && cudaMemcpy(hc.data(), d_c, sizeof(Cand) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
     cudaFree(d_c); cudaFree(d_s); cudaFree(d_ns);
     if (rc) return set_error(c, rc, "CUDA failure in debug eliminate");
@@ -1128,14 +1218,16 @@ int sift_gpu_debug_eliminate(sift_gpu_ctx* c, const float* d0, const float* d1, 
 
 int sift_gpu_debug_get_candidates(sift_gpu_ctx* c, int image_idx, uint16_t* xs, uint16_t* ys, uint16_t* octave, uint16_t* index,
                                   uint8_t* filtered, uint32_t capacity, uint32_t* n_out) {
-    if (!c || !c->last_plan || image_idx < 0 || image_idx >= c->last_batch || !n_out) return set_error(c, SIFT_GPU_E_INVALID, "bad argument");
+    if (!c || c->last_slot < 0 || image_idx < 0 || image_idx >= (int)c->slots[c->last_slot].imgs.size() || !n_out)
+        return set_error(c, SIFT_GPU_E_INVALID, "bad argument");
+    const Slot& S = c->slots[c->last_slot];
     CTX_CUDA(cudaSetDevice(c->prm.device));
     uint32_t n = 0;
-    CTX_CUDA(cudaMemcpy(&n, c->d_n_cand + image_idx, sizeof n, cudaMemcpyDeviceToHost));
+    CTX_CUDA(cudaMemcpy(&n, S.d_n_cand + image_idx, sizeof n, cudaMemcpyDeviceToHost));
     *n_out = n;
     const uint32_t m = std::min(n, capacity);
     std::vector<Cand> hc(m);
-    if (m) CTX_CUDA(cudaMemcpy(hc.data(), c->d_cands + (size_t)image_idx * c->cand_cap, sizeof(Cand) * m, cudaMemcpyDeviceToHost));
+    if (m) CTX_CUDA(cudaMemcpy(hc.data(), S.d_cands + (size_t)image_idx * c->cand_cap, sizeof(Cand) * m, cudaMemcpyDeviceToHost));
     for (uint32_t i = 0; i < m; ++i) {
         if (xs) xs[i] = hc[i].x;
         if (ys) ys[i] = hc[i].y;
