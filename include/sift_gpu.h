@@ -139,6 +139,9 @@ int sift_gpu_debug_get_candidates(sift_gpu_ctx* ctx, int image_idx, uint16_t* xs
                                   uint16_t* index, uint8_t* filtered, uint32_t capacity, uint32_t* n);
 /* The std::sort(cmpByFilter) permutation the host replays (sift.cpp:37): order[i] = source index. */
 int sift_gpu_debug_sort_order(const uint8_t* filtered, uint32_t n, uint32_t* order);
+/* The same permutation restricted to the unfiltered elements (all the pipeline needs), computed by the sparse
+ * introsort simulation the product path uses: unfiltered_order[i] = source index of the i-th element after the sort. */
+int sift_gpu_debug_sort_order_fast(const uint8_t* filtered, uint32_t n, uint32_t* unfiltered_order, uint32_t* n_unfiltered);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,8 @@ def load():
                                                 C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.sift_gpu_debug_sort_order.restype = C.c_int
     L.sift_gpu_debug_sort_order.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.sift_gpu_debug_sort_order_fast.restype = C.c_int
+    L.sift_gpu_debug_sort_order_fast.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -108,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "sift_gpu_create", "sift_gpu_run", "sift_gpu_destroy", "sift_gpu_last_error", "sift_gpu_get_timings",
     "sift_gpu_version", "sift_gpu_debug_get_level", "sift_gpu_debug_blur", "sift_gpu_debug_reduce",
     "sift_gpu_debug_increase", "sift_gpu_debug_extrema", "sift_gpu_debug_eliminate", "sift_gpu_debug_get_candidates",
-    "sift_gpu_debug_sort_order",
+    "sift_gpu_debug_sort_order", "sift_gpu_debug_sort_order_fast",
 ]
 
 
@@ -120,6 +122,17 @@ def sort_order(flags):
     if rc != 0:
         raise SiftGpuError(rc, "sort_order")
     return order
+
+
+def sort_order_fast(flags):
+    """Post-sort order of the unfiltered elements from the sparse introsort simulation (order_replay.h)."""
+    flags = np.ascontiguousarray(flags, np.uint8)
+    order = np.zeros(max(1, flags.size), np.uint32)
+    n = C.c_uint32()
+    rc = load().sift_gpu_debug_sort_order_fast(flags.ctypes.data, flags.size, order.ctypes.data, C.byref(n))
+    if rc != 0:
+        raise SiftGpuError(rc, "sort_order_fast")
+    return order[: n.value].copy()
 
 
 class SiftGpu:

@@ -22,6 +22,7 @@
 
 #include "../../include/sift_gpu.h"
 #include "common.cuh"
+#include "order_replay.h"
 #include "tma.cuh"
 
 namespace siftgpu {
@@ -613,19 +614,18 @@ static int run_pyramid(sift_gpu_ctx* c, Slot& S, const Plan* p, const PlanSlot& 
 
 // The reference's cleanup (sift.cpp:37-42): std::sort with cmpByFilter, count of leading unfiltered
 // truncated to u16.  `flags[i]` = filtered; returns the kept source indices in their new order.
-static void cleanup_order(const std::vector<uint8_t>& flags, bool canonical, std::vector<uint32_t>* kept) {
-    const size_t n = flags.size();
-    std::vector<uint32_t> v(n);
-    for (size_t i = 0; i < n; ++i) v[i] = (uint32_t)i | (flags[i] ? 0x80000000u : 0u);
-    if (canonical)
-        std::stable_partition(v.begin(), v.end(), [](uint32_t a) { return !(a >> 31); });
-    else
-        std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
-    size_t unf = 0;
-    while (unf < n && !(v[unf] >> 31)) ++unf;
-    const uint16_t size = (uint16_t)unf;
-    kept->resize(size);
-    for (size_t i = 0; i < size; ++i) (*kept)[i] = v[i] & 0x7fffffffu;
+// `zero_pos`: ascending positions of the unfiltered elements of an n-element vector.  Returns the kept elements, as
+// indices into zero_pos, in their post-sort order.  The std::sort permutation is replayed by SparseFilterSort
+// (order_replay.h); the canonical mode keeps the original order (what a stable partition would do).
+static void cleanup_order(uint32_t n, const std::vector<uint32_t>& zero_pos, bool canonical, std::vector<uint32_t>* kept) {
+    static thread_local SparseFilterSort sorter;
+    if (canonical) {
+        kept->resize(zero_pos.size());
+        for (size_t i = 0; i < zero_pos.size(); ++i) (*kept)[i] = (uint32_t)i;
+    } else {
+        *kept = sorter.run(n, zero_pos);
+    }
+    kept->resize((uint16_t)zero_pos.size());  // u16_t size = distance(begin, first filtered) (sift.cpp:41)
 }
 
 // Host half of Sift::calculate between _eliminateEdgeResponses and _createDecriptors (sift.cpp:37-55).
@@ -638,36 +638,31 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
     // first cleanup over all candidates
     std::vector<uint32_t> L1;  // survivor slots in vector order
     {
-        std::vector<uint32_t> v(n_cand, 0x80000000u);
-        for (uint32_t s = 0; s < n_surv; ++s) v[S[s].canon] = s;
-        if (canonical)
-            std::stable_partition(v.begin(), v.end(), [](uint32_t a) { return !(a >> 31); });
-        else
-            std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
-        const uint16_t size = (uint16_t)n_surv;  // u16_t size = distance(...) (sift.cpp:41)
-        L1.assign(v.begin(), v.begin() + size);
+        std::vector<uint32_t> zero_pos(n_surv);
+        for (uint32_t s = 0; s < n_surv; ++s) zero_pos[s] = S[s].canon;
+        cleanup_order(n_cand, zero_pos, canonical, &L1);
     }
     out->n_survivors = (uint32_t)L1.size();
     // _orientationAssignment bounds test (sift.cpp:173-178) and the dead blur's precondition (sift.cpp:184)
-    std::vector<uint8_t> flags2(L1.size());
+    std::vector<uint32_t> inside;  // positions in L1 that pass the bounds test
     for (size_t i = 0; i < L1.size(); ++i) {
         const Surv& s = S[L1[i]];
         const int slot = p->class_target[(size_t)(s.octave * D + s.index)];
         const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
         const bool outside = (s.x < kRegion || s.x >= tw - kRegion) || (s.y < kRegion || s.y >= th - kRegion);
-        flags2[i] = outside ? 1 : 0;
+        if (!outside) inside.push_back((uint32_t)i);
         if (!outside && (c->prm.flags & SIFT_GPU_FLAG_STRICT) && 2 * kRegion < c->dead_blur_r[s.octave][s.index] + 1) {
             out->status = SIFT_GPU_E_PRECONDITION;
             return;
         }
     }
-    std::vector<uint32_t> L2;
-    cleanup_order(flags2, canonical, &L2);
+    std::vector<uint32_t> L2;  // indices into `inside`
+    cleanup_order((uint32_t)L1.size(), inside, canonical, &L2);
     out->kps.resize(L2.size());
     out->key_of.assign(L2.size(), ~0u);
     out->keys.clear();
     for (size_t i = 0; i < L2.size(); ++i) {
-        const Surv& s = S[L1[L2[i]]];
+        const Surv& s = S[L1[inside[L2[i]]]];
         const int slot = p->class_target[(size_t)(s.octave * D + s.index)];
         const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
         sift_gpu_keypoint& k = out->kps[i];
@@ -1235,6 +1230,18 @@ int sift_gpu_debug_get_candidates(sift_gpu_ctx* c, int image_idx, uint16_t* xs, 
         if (index) index[i] = hc[i].index;
         if (filtered) filtered[i] = hc[i].filtered;
     }
+    return SIFT_GPU_OK;
+}
+
+int sift_gpu_debug_sort_order_fast(const uint8_t* filtered, uint32_t n, uint32_t* unfiltered_order, uint32_t* n_unfiltered) {
+    if ((n && !filtered) || !unfiltered_order || !n_unfiltered) return SIFT_GPU_E_INVALID;
+    std::vector<uint32_t> zero_pos;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!filtered[i]) zero_pos.push_back(i);
+    SparseFilterSort sorter;
+    std::vector<uint32_t> order = sorter.run(n, zero_pos);
+    for (size_t i = 0; i < order.size(); ++i) unfiltered_order[i] = zero_pos[order[i]];
+    *n_unfiltered = (uint32_t)order.size();
     return SIFT_GPU_OK;
 }
 

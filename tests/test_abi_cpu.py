@@ -63,6 +63,32 @@ def test_host_sort_replay_equals_oracle(built):
         assert np.array_equal(capi.sort_order(flags), ol.sort_order(flags)), (n, keep)
 
 
+def test_sparse_sort_simulation_equals_std_sort(built):
+    """The product replays libstdc++'s introsort on the sparse set of unfiltered positions (order_replay.h); the order
+    it returns must be exactly where the real std::sort(cmpByFilter) puts the unfiltered elements."""
+    from sift_b200 import capi
+
+    rng = np.random.default_rng(1)
+    cases = 0
+    for n in list(range(0, 40)) + [63, 64, 65, 127, 129, 1000, 1025, 4096, 30000, 140000]:
+        for keep in (0.0, 0.015, 0.06, 0.3, 0.5, 0.9, 1.0):
+            for _ in range(2 if n > 2000 else 4):
+                flags = (rng.uniform(size=n) >= keep).astype(np.uint8)
+                full, fast = capi.sort_order(flags), capi.sort_order_fast(flags)
+                assert np.array_equal(full[: int((flags == 0).sum())], fast), (n, keep)
+                cases += 1
+    for n in (17, 33, 100, 1000, 5000):  # structured patterns: long runs push the partition into its corner cases
+        for pat in range(5):
+            f = np.ones(n, np.uint8)
+            if pat == 0: f[::2] = 0
+            if pat == 1: f[(np.arange(n) // 7) % 2 == 0] = 0
+            if pat == 2: f[n // 2:] = 0
+            if pat == 3: f[: n // 2] = 0
+            if pat == 4: f[n // 3: 2 * n // 3] = 0
+            assert np.array_equal(capi.sort_order(f)[: int((f == 0).sum())], capi.sort_order_fast(f)), (n, pat)
+    assert cases > 400
+
+
 def test_cpp_host_layer_is_built(built):
     for f in ("libsift_host.so", "sift"):
         assert os.path.exists(os.path.join(ROOT, "sift_b200", f))
