@@ -222,6 +222,31 @@ __device__ __noinline__ void issue_chunk_tma(float* dst, uint64_t* bar, const CU
     }
 }
 
+// Column-pass window: rows ub .. ub+WL-1 (mod RING) of this lane's two columns.  ub only takes RING/CH values
+// (it advances by CH per chunk), so each value gets its own fully static load sequence.
+template <int R, int M>
+__device__ __forceinline__ void load_window_phase(const float* ring_col, float2 (&win)[SC<R>::WL]) {
+    using C = SC<R>;
+    constexpr int UB = (C::RC - R + C::CH * M) % C::RING;
+#pragma unroll
+    for (int k = 0; k < C::WL; ++k) win[k] = *reinterpret_cast<const float2*>(ring_col + ((UB + k) % C::RING) * C::WC);
+}
+template <int R>
+__device__ __forceinline__ void load_window(int phase, const float* ring_col, float2 (&win)[SC<R>::WL]) {
+    constexpr int NP = SC<R>::RING / SC<R>::CH;
+    static_assert(NP <= 8, "add cases");
+    switch (phase) {
+        case 0: load_window_phase<R, 0>(ring_col, win); break;
+        case 1: if (NP > 1) load_window_phase<R, 1 % NP>(ring_col, win); break;
+        case 2: if (NP > 2) load_window_phase<R, 2 % NP>(ring_col, win); break;
+        case 3: if (NP > 3) load_window_phase<R, 3 % NP>(ring_col, win); break;
+        case 4: if (NP > 4) load_window_phase<R, 4 % NP>(ring_col, win); break;
+        case 5: if (NP > 5) load_window_phase<R, 5 % NP>(ring_col, win); break;
+        case 6: if (NP > 6) load_window_phase<R, 6 % NP>(ring_col, win); break;
+        default: if (NP > 7) load_window_phase<R, 7 % NP>(ring_col, win); break;
+    }
+}
+
 template <int R, bool FMA, bool DECIMATE>
 __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__ CUtensorMap map8, const __grid_constant__ CUtensorMap map1,
                                                          const StreamArgs sa, const TapsP<R> taps) {
@@ -271,25 +296,36 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
     const float* const src_col = src + (active ? x : 0);
     const float* const ring_col = ring + 2 * lane;
 
+    // running row pointers of the output chunk (advance by 8 rows per chunk; rows inside a chunk add a multiple of the pitch)
+    float* dst_row = dst_col ? dst_col + (size_t)y0 * a.dst_pitch : nullptr;
+    float* dog_row = dog_col ? dog_col + (size_t)y0 * a.dog_pitch : nullptr;
+    const float* low_row = src_col + (size_t)y0 * a.src_pitch;   // centre values of the chunk whose `lower` is fetched next
+    const size_t dstp = (size_t)a.dst_pitch, dogp = (size_t)a.dog_pitch, srcp = (size_t)a.src_pitch;
     // DoG centre values of the next output chunk, fetched one chunk ahead so their latency never shows
     float2 lower[C::CH];
-    auto fetch_lower = [&](int jn) {
+    auto fetch_lower = [&](int rows_left) {
+        if (rows_left >= C::CH) {
 #pragma unroll
-        for (int o = 0; o < C::CH; ++o) lower[o] = *reinterpret_cast<const float2*>(src_col + min(y0 + jn * C::CH + o, y1 - 1) * a.src_pitch);
+            for (int o = 0; o < C::CH; ++o) lower[o] = *reinterpret_cast<const float2*>(low_row + o * srcp);
+        } else {
+#pragma unroll
+            for (int o = 0; o < C::CH; ++o) lower[o] = *reinterpret_cast<const float2*>(low_row + (size_t)min(o, rows_left - 1) * srcp);
+        }
+        low_row += C::CH * srcp;
     };
-    if (!DECIMATE && dog_col) fetch_lower(0);
+    if (!DECIMATE && dog_col && active) fetch_lower(y1 - y0);
 
     int s = 0;                              // staging stage of chunk i and its mbarrier phase parity
     uint32_t parity = 0;
     int wslot = 0;                          // ring slot of the chunk being row-filtered
-    int ub = (C::RC - R) % C::RING;         // ring slot of the first window row of the next output chunk
+    int phase = 0;                          // output chunk index mod RING/CH: selects the static window-load sequence
 #pragma unroll 1
     for (int i = 0; i < n_in; ++i) {
         float* const st = stage + s * C::CH * C::SWW;
         tma::mbar_wait(&full[s], parity);
         if (edge) patch_reflected_columns(st, w, xs, C::RPAD, R, C::SWW, lane);
         // ---- row pass ----
-#pragma unroll 1
+#pragma unroll 2
         for (int q = 0; q < 4; ++q) {
             const int rr = rsub + 2 * q;
             const float* srow = st + rr * C::SWW + 4 * cg;
@@ -308,8 +344,15 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
         }
         wslot = wslot + C::CH == C::RING ? 0 : wslot + C::CH;
         __syncwarp();  // ring rows of chunk i visible to the warp; every lane is done with stage s
-        if (lane == 0 && i + C::NS < n_in)
-            issue_chunk_tma(st, &full[s], &map8, &map1, xs - C::RPAD, y0 - C::RC + (i + C::NS) * C::CH, h, b, C::SWW);
+        if (lane == 0 && i + C::NS < n_in) {
+            const int v0 = y0 - C::RC + (i + C::NS) * C::CH;
+            if (v0 >= 0 && v0 + C::CH <= h) {
+                tma::mbar_arrive_expect_tx(&full[s], C::CH * C::SWW * (int)sizeof(float));
+                tma::load_3d(st, &map8, &full[s], xs - C::RPAD, v0, b);
+            } else {
+                issue_chunk_tma(st, &full[s], &map8, &map1, xs - C::RPAD, v0, h, b, C::SWW);
+            }
+        }
         // ---- column pass for output chunk j = i - LAG ----
         const int j = i - C::LAG;
         if (j >= 0) {
@@ -317,18 +360,7 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
                 const int yb = y0 + j * C::CH;
                 const int nrows = y1 - yb;  // >= 1; a full chunk unless this is the segment's last one
                 float2 win[C::WL];
-                if (ub + C::WL <= C::RING) {
-                    const float* p0 = ring_col + ub * C::WC;
-#pragma unroll
-                    for (int k = 0; k < C::WL; ++k) win[k] = *reinterpret_cast<const float2*>(p0 + k * C::WC);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < C::WL; ++k) {
-                        int sl = ub + k;
-                        sl = sl >= C::RING ? sl - C::RING : sl;
-                        win[k] = *reinterpret_cast<const float2*>(ring_col + sl * C::WC);
-                    }
-                }
+                load_window<R>(phase, ring_col, win);
                 if (!DECIMATE) {
                     float2 acc[C::CH];
 #pragma unroll
@@ -336,18 +368,31 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
 #pragma unroll
                         for (int o = 0; o < C::CH; ++o) acc[o] = jj == 0 ? __fmul2_rn(taps.dup[0], win[o]) : tap_acc2<FMA>(acc[o], taps.dup[jj], win[o + jj]);
                     }
-                    if (dst_col) {
+                    if (nrows >= C::CH) {  // full chunk: no per-row predicates
+                        if (dst_col) {
 #pragma unroll
-                        for (int o = 0; o < C::CH; ++o)
-                            if (o < nrows) *reinterpret_cast<float2*>(dst_col + (yb + o) * a.dst_pitch) = acc[o];
-                    }
-                    if (dog_col) {
+                            for (int o = 0; o < C::CH; ++o) *reinterpret_cast<float2*>(dst_row + o * dstp) = acc[o];
+                        }
+                        if (dog_col) {
 #pragma unroll
-                        for (int o = 0; o < C::CH; ++o)
-                            if (o < nrows)
-                                *reinterpret_cast<float2*>(dog_col + (yb + o) * a.dog_pitch) =
+                            for (int o = 0; o < C::CH; ++o)
+                                *reinterpret_cast<float2*>(dog_row + o * dogp) =
                                     make_float2(__fadd_rn(128.0f, __fsub_rn(acc[o].x, lower[o].x)), __fadd_rn(128.0f, __fsub_rn(acc[o].y, lower[o].y)));
-                        if (j + 1 < n_out_chunks) fetch_lower(j + 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < C::CH; ++o)
+                            if (o < nrows) {
+                                if (dst_col) *reinterpret_cast<float2*>(dst_row + o * dstp) = acc[o];
+                                if (dog_col)
+                                    *reinterpret_cast<float2*>(dog_row + o * dogp) =
+                                        make_float2(__fadd_rn(128.0f, __fsub_rn(acc[o].x, lower[o].x)), __fadd_rn(128.0f, __fsub_rn(acc[o].y, lower[o].y)));
+                            }
+                    }
+                    if (dst_col) dst_row += C::CH * dstp;
+                    if (dog_col) {
+                        dog_row += C::CH * dogp;
+                        if (j + 1 < n_out_chunks) fetch_lower(nrows - C::CH);
                     }
                 } else {
 #pragma unroll
@@ -363,7 +408,7 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
                     }
                 }
             }
-            ub = ub + C::CH >= C::RING ? ub + C::CH - C::RING : ub + C::CH;
+            phase = phase + 1 == C::RING / C::CH ? 0 : phase + 1;
         }
         if (++s == C::NS) { s = 0; parity ^= 1u; }
     }
