@@ -119,7 +119,7 @@ struct SC {
     static constexpr int CH = 8;        // rows per chunk
     static constexpr int WC = 64;       // columns per warp
     static constexpr int NWARP = 2;     // warps per CTA (adjacent strips); small CTAs pack shared memory better
-    static constexpr int NS = 3;        // staging stages per warp (TMA runs two chunks ahead)
+    static constexpr int NS = 2;        // staging stages per warp (TMA runs one chunk ahead)
     static constexpr int RPAD = (R + 3) & ~3;
     static constexpr int SWW = (WC + 2 * RPAD <= 96) ? 96 : 128;   // staged floats per row (128-B multiple)
     static constexpr int RC = ((R + CH - 1) / CH) * CH;             // rows loaded above the first output row
