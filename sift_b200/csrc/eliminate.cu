@@ -48,28 +48,31 @@ __global__ void __launch_bounds__(128) eliminate_kernel(const ScanLayer* __restr
             const float dxs = (AT(D2, x + 1, y) - AT(D2, x - 1, y) - AT(D0, x + 1, y) + AT(D0, x - 1, y)) / 2;
             const float dys = (AT(D2, x, y + 1) - AT(D2, x, y + 1) - AT(D0, x, y + 1) + AT(D0, x, y - 1)) / 2;
 #undef AT
-            const float H[9] = {dxx, dxy, dxs, dxy, dyy, dys, dxs, dys, dss};
-            float negH[9], inv[9], ext[3];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) negH[k] = H[k] * -1.0f;
-            const float grad[3] = {dx, dy, ds};
+            // The reference tests in the order inverse / solve / ext > 127.5 / contrast / det < 0 / edge ratio and stops at the
+            // first hit; the verdict is the OR of all of them, so the two tests that need no linear algebra run first.
             bool filtered = false;
-            if (!qr::inverse3(negH, inv)) filtered = true;
-            if (!filtered && !qr::solve3(inv, grad, ext)) filtered = true;
-            if (!filtered && ((double)ext[0] > 127.5 || (double)ext[1] > 127.5 || (double)ext[2] > 127.5)) filtered = true;
-            if (!filtered) {
-                float f = 0.0f;
-                f = f + grad[0] * ext[0];
-                f = f + grad[1] * ext[1];
-                f = f + grad[2] * ext[2];
-                f = (float)((double)f * (0.5 + (double)c11));
-                if ((double)f < 7.65) filtered = true;
-            }
-            if (!filtered) {
+            {
                 const float tr = dxx + dyy;
                 const float det = (float)((double)(dxx * dyy) - (double)dxy * (double)dxy);
                 if (det < 0) filtered = true;
                 else if (((double)tr * (double)tr) / (double)det > (double)t) filtered = true;
+            }
+            if (!filtered) {
+                const float negH[9] = {dxx * -1.0f, dxy * -1.0f, dxs * -1.0f, dxy * -1.0f, dyy * -1.0f, dys * -1.0f,
+                                       dxs * -1.0f, dys * -1.0f, dss * -1.0f};
+                const float grad[3] = {dx, dy, ds};
+                float inv[9], ext[3];
+                if (!qr::inverse3_fast(negH, inv)) filtered = true;
+                if (!filtered && !qr::solve3_fullrank(inv, grad, ext)) filtered = true;
+                if (!filtered && ((double)ext[0] > 127.5 || (double)ext[1] > 127.5 || (double)ext[2] > 127.5)) filtered = true;
+                if (!filtered) {
+                    float f = 0.0f;
+                    f = f + grad[0] * ext[0];
+                    f = f + grad[1] * ext[1];
+                    f = f + grad[2] * ext[2];
+                    f = (float)((double)f * (0.5 + (double)c11));
+                    if ((double)f < 7.65) filtered = true;
+                }
             }
             keep = !filtered;
             cl[i].filtered = filtered ? 1 : 0;

@@ -121,20 +121,33 @@ __global__ void __launch_bounds__(1024) column_scan_kernel(const uint32_t* __res
     if (threadIdx.x == 0) n_cand[b] = carry;
 }
 
-// (D) one thread per global column: expand the bit words top to bottom.
-__global__ void extrema_emit_kernel(const ScanLayer* __restrict__ layers, int n_layers, int total_cols,
-                                    const uint32_t* __restrict__ mask, uint32_t mask_words_per_image,
-                                    const uint32_t* __restrict__ col_off, Cand* __restrict__ cands, size_t cand_stride) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// (D) one warp per global column: lane l owns mask word l (32 rows each); a warp prefix sum of the popcounts gives
+// every lane its slot, so the column's candidates come out top to bottom.
+__global__ void __launch_bounds__(256) extrema_emit_kernel(const ScanLayer* __restrict__ layers, int n_layers, int total_cols,
+                                                           const uint32_t* __restrict__ mask, uint32_t mask_words_per_image,
+                                                           const uint32_t* __restrict__ col_off, Cand* __restrict__ cands,
+                                                           size_t cand_stride) {
+    const int lane = threadIdx.x & 31;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int b = blockIdx.y;
     if (g >= total_cols) return;
     const int li = find_layer(layers, n_layers, (uint32_t)g);
     const ScanLayer L = layers[li];
     const int x = g - (int)L.col_base;
     const uint32_t* m = mask + (size_t)b * mask_words_per_image + L.mask_off + x;
-    Cand* out = cands + (size_t)b * cand_stride + col_off[(size_t)b * total_cols + g];
-    for (int yw = 0; yw < L.n_yw; ++yw) {
-        uint32_t word = m[(size_t)yw * L.w];
+    uint32_t base = col_off[(size_t)b * total_cols + g];
+    Cand* out = cands + (size_t)b * cand_stride;
+    for (int yw0 = 0; yw0 < L.n_yw; yw0 += 32) {
+        const int yw = yw0 + lane;
+        uint32_t word = yw < L.n_yw ? m[(size_t)yw * L.w] : 0u;
+        const uint32_t cnt = (uint32_t)__popc(word);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t slot = base + incl - cnt;
         while (word) {
             const int k = __ffs(word) - 1;
             word &= word - 1;
@@ -145,8 +158,9 @@ __global__ void extrema_emit_kernel(const ScanLayer* __restrict__ layers, int n_
             c.index = L.index;
             c.filtered = 0;
             c.pad = 0;
-            *out++ = c;
+            out[slot++] = c;
         }
+        base += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -162,8 +176,9 @@ int launch_extrema(const ScanLayer* layers_dev, const ScanLayer* layers_host, in
     dim3 gcol((total_cols + 127) / 128, batch);
     extrema_count_kernel<<<gcol, 128, 0, s>>>(layers_dev, n_layers, total_cols, mask, mask_words_per_image, col_count);
     column_scan_kernel<<<batch, 1024, 0, s>>>(col_count, total_cols, col_off, n_cand);
-    extrema_emit_kernel<<<gcol, 128, 0, s>>>(layers_dev, n_layers, total_cols, mask, mask_words_per_image, col_off, cands,
-                                             cand_stride);
+    dim3 gwarp((total_cols + 7) / 8, batch);  // 8 warps (columns) per CTA
+    extrema_emit_kernel<<<gwarp, 256, 0, s>>>(layers_dev, n_layers, total_cols, mask, mask_words_per_image, col_off, cands,
+                                              cand_stride);
     if (launches) *launches += 3;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;

@@ -33,7 +33,9 @@ __device__ __forceinline__ void gradient_at(const float* __restrict__ G, int pit
     *mag = (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
     const float r = atan2f(dy, dx);
     const float s = r + 360.0f;
-    *ori = (float)fmod((double)s, 360.0);
+    // (float)fmod((double)s, 360.0): s lies in [360-pi, 360+pi], where the remainder is s or s - 360, and s - 360 is exact
+    // in fp32 (s is a multiple of 2^-15 and the difference is below 4)
+    *ori = s >= 360.0f ? s - 360.0f : s;
 }
 
 // alg::vertexParabola (algorithms.cpp:153-178).
@@ -43,14 +45,13 @@ __device__ float vertex_parabola(int lx, float ly, int px, float py, int rx, flo
     a[3] = (float)((double)px * (double)px); a[4] = (float)px; a[5] = 0.0f;
     a[6] = (float)((double)rx * (double)rx); a[7] = (float)rx; a[8] = 0.0f;
     b[0] = ly; b[1] = py; b[2] = ry;
-    qr::solve3(a, b, res);
+    qr::solve3_fast(a, b, res);
     return -res[1] / (2 * res[0]);
 }
 
 // Sift::_findPeaks (sift.cpp:220-286).  Emulates std::set<float>: sorted, unique; a NaN is only
 // ever kept when it is the first value inserted, and then nothing else is.
-__device__ int find_peaks(const float* histo, float* out) {
-    float p[36];
+__device__ int find_peaks(const float* histo, float* p, float* out) {
     int max_index = 0;
     for (int i = 0; i < 36; ++i) p[i] = histo[i];
     for (int i = 1; i < 36; ++i)
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(128) orientation_kernel(const LevelRef* __rest
     __shared__ float s_val[4][kWin * kWin];
     __shared__ uint16_t s_bin[4][kWin * kWin];
     __shared__ float s_hist[4][36];
+    __shared__ float s_work[4][36], s_out[4][36];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_keys; k += warps) {
@@ -119,14 +121,15 @@ __global__ void __launch_bounds__(128) orientation_kernel(const LevelRef* __rest
         __syncwarp();
         for (int bin = lane; bin < 36; bin += 32) {
             float acc = 0.0f;
+#pragma unroll 8
             for (int s = 0; s < kWin * kWin; ++s)
                 if (s_bin[wib][s] == bin) acc = acc + s_val[wib][s];
             s_hist[wib][bin] = acc;
         }
         __syncwarp();
         if (lane == 0) {
-            float out[36];
-            const int n = find_peaks(s_hist[wib], out);
+            float* out = s_out[wib];
+            const int n = find_peaks(s_hist[wib], s_work[wib], out);
             orientation[k] = out[0];
             n_peaks[k] = (uint32_t)n;
             if (n > 1)
