@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) orientation_kernel(const LevelRef* __rest
                                                           const uint32_t* __restrict__ key_img, uint32_t n_keys,
                                                           float* __restrict__ orientation, uint32_t* __restrict__ n_peaks,
                                                           float* __restrict__ peaks) {
-    __shared__ float s_val[4][kWin * kWin];
+    __shared__ __align__(16) float s_val[4][kWin * kWin];
     __shared__ uint16_t s_bin[4][kWin * kWin];
     __shared__ float s_hist[4][36];
     __shared__ float s_work[4][36], s_out[4][36];
@@ -109,22 +109,53 @@ __global__ void __launch_bounds__(128) orientation_kernel(const LevelRef* __rest
         const float* G = T.base + (size_t)key_img[k] * T.stride;
         const int x0 = key.x - kRegion, y0 = key.y - kRegion;
         // sample s = wx*16 + wy is the reference's (x outer, y inner) visiting order
-        for (int s = lane; s < kWin * kWin; s += 32) {
+        bool same_bin = true;  // do all 256 samples fall into the bin of sample 0?
+        uint16_t bin0 = 0;
+#pragma unroll
+        for (int j = 0; j < (kWin * kWin) / 32; ++j) {
+            const int s = lane + 32 * j;
             const int wx = s >> 4, wy = s & 15;
             float mag, ori;
             gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &mag, &ori);
             const float g = G[(size_t)(y0 + wy) * T.pitch + x0 + wx];
             s_val[wib][s] = mag * g;
             uint16_t bi = (uint16_t)(int)floorf(ori / 10);
-            s_bin[wib][s] = bi % 35;
+            bi = bi % 35;
+            s_bin[wib][s] = bi;
+            if (j == 0) bin0 = (uint16_t)__shfl_sync(0xffffffffu, (int)bi, 0);
+            same_bin = same_bin && bi == bin0;
         }
+        same_bin = __all_sync(0xffffffffu, same_bin);
         __syncwarp();
-        for (int bin = lane; bin < 36; bin += 32) {
-            float acc = 0.0f;
-#pragma unroll 8
-            for (int s = 0; s < kWin * kWin; ++s)
-                if (s_bin[wib][s] == bin) acc = acc + s_val[wib][s];
-            s_hist[wib][bin] = acc;
+        if (same_bin) {
+            // Every sample lands in one bin (with the reference's radians-as-degrees binning that is always bin 0):
+            // its sum is the plain sequential sum of the 256 products in visiting order; the other 35 bins are 0.
+            if (lane < 4) s_hist[wib][32 + lane] = 0.0f;
+            s_hist[wib][lane] = 0.0f;
+            __syncwarp();
+            if (lane == 0) {
+                float acc = 0.0f;
+                const float4* v4 = reinterpret_cast<const float4*>(s_val[wib]);
+#pragma unroll 4
+                for (int q = 0; q < (kWin * kWin) / 4; ++q) {
+                    const float4 v = v4[q];
+                    acc = acc + v.x; acc = acc + v.y; acc = acc + v.z; acc = acc + v.w;
+                }
+                s_hist[wib][bin0] = acc;
+            }
+        } else {
+            // general case: lane b owns bin b (lanes 0..3 also bins 32..35) and walks the samples in visiting order
+            float acc0 = 0.0f, acc1 = 0.0f;
+            const int binb = 32 + lane;
+#pragma unroll 4
+            for (int s = 0; s < kWin * kWin; ++s) {
+                const int bi = s_bin[wib][s];
+                const float v = s_val[wib][s];
+                if (bi == lane) acc0 = acc0 + v;
+                if (bi == binb) acc1 = acc1 + v;
+            }
+            s_hist[wib][lane] = acc0;
+            if (lane < 4) s_hist[wib][binb] = acc1;
         }
         __syncwarp();
         if (lane == 0) {
@@ -198,12 +229,22 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
         }
         // replay earlier keypoints of this image and level whose window overlaps, in vector order
         const uint32_t first = key_first[img];
-        for (uint32_t base = first; base < k; base += 32) {
+        constexpr int kAhead = 4;  // key chunks loaded per step: their global-load latencies overlap
+        for (uint32_t base0 = first; base0 < k; base0 += 32 * kAhead) {
+            KeyIn kmv[kAhead];
+#pragma unroll
+            for (int c = 0; c < kAhead; ++c) {
+                const uint32_t m = base0 + 32 * c + lane;
+                kmv[c] = keys[m < k ? m : k];
+            }
+#pragma unroll
+            for (int c = 0; c < kAhead; ++c) {
+            const uint32_t base = base0 + 32 * c;
+            if (base >= k) break;
             const uint32_t m = base + lane;
+            const KeyIn km = kmv[c];
             bool hit = false;
-            KeyIn km;
             if (m < k) {
-                km = keys[m];
                 const int ddx = (int)km.x - (int)key.x, ddy = (int)km.y - (int)key.y;
                 hit = km.tgt == key.tgt && ddx > -kWin && ddx < kWin && ddy > -kWin && ddy < kWin;
             }
@@ -223,6 +264,7 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
                         M[j] = M[j] + W[ly * kWin + lx];
                     }
                 }
+            }
             }
         }
         const float theta = orientation[k];
