@@ -171,18 +171,19 @@ def run_ours(args):
     g = capi.SiftGpu(DPE, OCTAVES, 1.6, capi.SQRT2_F32, False, max_width=W, max_height=H, max_batch=args.device_batch,
                      device=local_rank, flags=args.flags)
 
-    def descs(base_ptr, memory, step):
+    def descs(base_ptr, memory, step, dtype=capi.DTYPE_F32):
         arr = (capi.Image * B)()
+        esz = 4 if dtype == capi.DTYPE_F32 else 1
         for j in range(B):
             f = (step * B + j) % n_distinct
-            arr[j] = capi.Image(base_ptr + f * W * H * 4, W, H, 0, capi.DTYPE_F32, memory, None)
+            arr[j] = capi.Image(base_ptr + f * W * H * esz, W, H, 0, dtype, memory, None)
         return arr
 
-    def do_steps(base_ptr, memory, n_steps, first):
+    def do_steps(base_ptr, memory, n_steps, first, dtype=capi.DTYPE_F32):
         acc = {"pyramid_ms": 0.0, "span_ms": 0.0, "launches": 0, "kps": 0, "cands": 0, "surv": 0, "device_total_ms": 0.0,
                "host_order_ms": 0.0, "stages": {}}
         for s in range(n_steps):
-            rc, res = g.run_raw(descs(base_ptr, memory, first + s), B)
+            rc, res = g.run_raw(descs(base_ptr, memory, first + s, dtype), B)
             if rc != 0:
                 raise g._err(rc)
             t = g.timings()
@@ -195,8 +196,8 @@ def run_ours(args):
                 acc["kps"] += r.n; acc["cands"] += r.n_candidates; acc["surv"] += r.n_survivors
         return acc
 
-    def timed(base_ptr, memory):
-        do_steps(base_ptr, memory, args.warmup, 0)
+    def timed(base_ptr, memory, dtype=capi.DTYPE_F32):
+        do_steps(base_ptr, memory, args.warmup, 0, dtype)
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
@@ -205,7 +206,7 @@ def run_ours(args):
             sampler.start()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        acc = do_steps(base_ptr, memory, args.steps, args.warmup)
+        acc = do_steps(base_ptr, memory, args.steps, args.warmup, dtype)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         if dist:
@@ -215,6 +216,10 @@ def run_ours(args):
 
     wall_d, acc_d, clocks = timed(dev_frames.data_ptr(), capi.MEM_DEVICE)
     wall_h, acc_h, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
+    # supplementary: the same frames as 8-bit pixels (what a decoder produces before Vigra's importImage widens them,
+    # main.cpp:52-54); the library widens on the device, results are identical, the upload is 4x smaller
+    host_u8 = host_frames.to(torch.uint8).pin_memory()
+    wall_u8, acc_u8, _ = timed(host_u8.data_ptr(), capi.MEM_HOST, capi.DTYPE_U8)
 
     # Roofline of the pyramid + DoG stage: in the pipelined runs above three device passes overlap, so a stage's
     # CUDA-event duration includes other passes' kernels.  Time the stage on a serial context (one pass at a time,
@@ -229,12 +234,12 @@ def run_ours(args):
 
     # run() is synchronous (it returns after its last stream sync), so the host clock around the K steps equals the
     # device-side span; span_ms (CUDA events on the library's stream) is reported beside it.  Max over ranks.
-    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_r["pyramid_ms"]],
+    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_r["pyramid_ms"], wall_u8],
                                     [args.steps * B, acc_d["launches"], acc_d["kps"], acc_d["cands"]])
     if rank != 0:
         g.close()
         return
-    wall_d, wall_h, span_d, pyr_ms = mx
+    wall_d, wall_h, span_d, pyr_ms, wall_u8 = mx
     images, launches, kps, cands = sm
     value = images / wall_d
     e2e = images / wall_h
@@ -266,6 +271,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * per_img_h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * wall_h / args.steps},
+        "e2e_u8_input": {"value": images / wall_u8, "unit": "images/s", "h2d_bytes_per_step": B * W * H, "ms_per_step": 1e3 * wall_u8 / args.steps,
+                         "note": "supplementary: same call with SIFT_GPU_DTYPE_U8 host frames (identical results)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "pyramid+DoG stage (blur/DoG/decimation launches of one device pass)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

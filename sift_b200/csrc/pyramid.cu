@@ -140,6 +140,7 @@ struct TapsP {           // tk[j] = kernel tap applied to source index x - R + j
     float2 dup[2 * R + 1];  // (tk[j], tk[j])
     float2 pe[R];           // (tk[2m], tk[2m+1])
     float2 po[R];           // (tk[2m+1], tk[2m+2])
+    float2 one;             // (1, 1), deliberately a run-time value: see tap_acc2
 };
 
 struct StreamArgs {
@@ -187,11 +188,13 @@ __device__ __forceinline__ float row_output(const float (&wv)[NWV], const TapsP<
 }
 
 template <bool FMA>
-__device__ __forceinline__ float2 tap_acc2(float2 acc, float2 t, float2 v) {
+__device__ __forceinline__ float2 tap_acc2(float2 acc, float2 t, float2 v, float2 one) {
     if (FMA) return __ffma2_rn(t, v, acc);
-    // exact: one packed multiply, two scalar adds (a packed add after a packed multiply would be contracted by ptxas)
+    // exact: the product is rounded by the packed multiply; the packed add is written as fma(m, 1, acc), which rounds
+    // m + acc exactly like an add.  A plain packed add after a packed multiply would be contracted into one FFMA2 by
+    // ptxas (single rounding) even with -fmad=false; `one` comes from the kernel parameters so nothing can fold it away.
     const float2 m = __fmul2_rn(t, v);
-    return make_float2(__fadd_rn(acc.x, m.x), __fadd_rn(acc.y, m.y));
+    return __ffma2_rn(m, one, acc);
 }
 
 // Reflect patch of one staged chunk (edge strips only): staged column c holds x = xs - rpad + c.  TMA zero-filled
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
 #pragma unroll
                     for (int jj = 0; jj <= 2 * R; ++jj) {
 #pragma unroll
-                        for (int o = 0; o < C::CH; ++o) acc[o] = jj == 0 ? __fmul2_rn(taps.dup[0], win[o]) : tap_acc2<FMA>(acc[o], taps.dup[jj], win[o + jj]);
+                        for (int o = 0; o < C::CH; ++o) acc[o] = jj == 0 ? __fmul2_rn(taps.dup[0], win[o]) : tap_acc2<FMA>(acc[o], taps.dup[jj], win[o + jj], taps.one);
                     }
                     if (nrows >= C::CH) {  // full chunk: no per-row predicates
                         if (dst_col) {
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
                         if (sy >= 0) {
                             float2 acc = __fmul2_rn(taps.dup[0], win[o]);
 #pragma unroll
-                            for (int jj = 1; jj <= 2 * R; ++jj) acc = tap_acc2<FMA>(acc, taps.dup[jj], win[o + jj]);
+                            for (int jj = 1; jj <= 2 * R; ++jj) acc = tap_acc2<FMA>(acc, taps.dup[jj], win[o + jj], taps.one);
                             if (sel0 >= 0) dst_col[sy * a.dst_pitch + sel0] = acc.x;
                             if (sel1 >= 0) dst_col[sy * a.dst_pitch + sel1] = acc.y;
                         }
@@ -466,6 +469,7 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
     dim3 grid(strips, (a.h + seg - 1) / seg, batch);
     TapsP<R> tp;
     auto tk = [&](int j) { return a.taps_host[2 * R - j]; };  // kernel walked from +r down while the source index ascends
+    tp.one = make_float2(1.0f, 1.0f);
     for (int j = 0; j < 2 * R + 1; ++j) tp.dup[j] = make_float2(tk(j), tk(j));
     for (int m = 0; m < R; ++m) {
         tp.pe[m] = make_float2(tk(2 * m), tk(2 * m + 1));
