@@ -87,6 +87,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // ---- launchers (each returns 0 or SIFT_GPU_E_CUDA; they count their launches in *launches) ----
 int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t* launches);
 int stream_box_width(int r);   // TMA box width the streaming kernel needs for radius r, or 0 if r has no streaming kernel
+int stream_box_rows();         // rows of the multi-row TMA box (the other descriptor has 1-row boxes)
 int max_generic_radius();      // largest radius the generic tile kernel can hold in shared memory
 int launch_resize_nn(const float* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int dw,
                      int dh, const int* map_x, const int* map_y, int batch, cudaStream_t s, uint64_t* launches);

@@ -119,7 +119,8 @@ struct SC {
     static constexpr int CH = 8;        // rows per chunk
     static constexpr int WC = 64;       // columns per warp
     static constexpr int NWARP = 2;     // warps per CTA (adjacent strips); small CTAs pack shared memory better
-    static constexpr int NS = 2;        // staging stages per warp (TMA runs one chunk ahead)
+    static constexpr int SR = 8;        // rows per staging stage (SR = 4 with NS = 3 was measured slower: more per-stage overhead)
+    static constexpr int NS = 2;        // staging stages per warp (TMA runs one stage ahead)
     static constexpr int RPAD = (R + 3) & ~3;
     static constexpr int SWW = (WC + 2 * RPAD <= 96) ? 96 : 128;   // staged floats per row (128-B multiple)
     static constexpr int RC = ((R + CH - 1) / CH) * CH;             // rows loaded above the first output row
@@ -128,11 +129,11 @@ struct SC {
     static constexpr int WL = CH + 2 * R;                           // column-pass window rows
     static constexpr int NW = 4 + 2 * RPAD;                         // row-pass window floats
     static constexpr int OFF = RPAD - R;
-    static constexpr int WARP_FLOATS = NS * CH * SWW + RING * WC;
+    static constexpr int WARP_FLOATS = NS * SR * SWW + RING * WC;
     static constexpr size_t SMEM = sizeof(float) * (size_t)(NWARP * WARP_FLOATS) + NWARP * NS * sizeof(uint64_t);
     static_assert(WC + 2 * RPAD <= SWW, "radius too large for the streaming kernel");
     static_assert(RING >= (LAG + 1) * CH - RC + R && RING % CH == 0 && RING >= WL, "ring too small");
-    static_assert((CH * SWW * 4) % 128 == 0 && (RING * WC * 4) % 128 == 0, "TMA destinations must stay 128-B aligned");
+    static_assert((SR * SWW * 4) % 128 == 0 && (RING * WC * 4) % 128 == 0 && CH % SR == 0, "TMA destinations must stay 128-B aligned");
 };
 
 template <int R>
@@ -200,9 +201,9 @@ __device__ __forceinline__ float2 tap_acc2(float2 acc, float2 t, float2 v, float
 // Reflect patch of one staged chunk (edge strips only): staged column c holds x = xs - rpad + c.  TMA zero-filled
 // what lies outside the image; columns -1..-r and w..w+r-1 get their mirrored pixels, which are staged in the same row
 // (x = -k mirrors to k <= r <= rpad + strip; x = w-1+k mirrors to w-1-k >= xs - rpad because rpad >= r and xs < w).
-__device__ __noinline__ void patch_reflected_columns(float* st, int w, int xs, int rpad, int r, int sww, int lane) {
+__device__ __noinline__ void patch_reflected_columns(float* st, int rows, int w, int xs, int rpad, int r, int sww, int lane) {
     const int n = 2 * r;  // per row: r columns left of 0, r columns right of w-1
-    for (int e = lane; e < 8 * n; e += 32) {
+    for (int e = lane; e < rows * n; e += 32) {
         const int rr = e / n, k = e - rr * n;
         const int gx = k < r ? -1 - k : w + (k - r);
         const int c = gx - (xs - rpad);
@@ -213,15 +214,15 @@ __device__ __noinline__ void patch_reflected_columns(float* st, int w, int xs, i
     __syncwarp();
 }
 
-// lane 0: fetch the 8 rows v0..v0+7 of columns [x, x + box) of image b into dst (one box when no row is reflected)
-__device__ __noinline__ void issue_chunk_tma(float* dst, uint64_t* bar, const CUtensorMap* map8, const CUtensorMap* map1, int x, int v0,
-                                             int h, int b, int sww) {
-    tma::mbar_arrive_expect_tx(bar, 8 * sww * (int)sizeof(float));
-    if (v0 >= 0 && v0 + 8 <= h) {
-        tma::load_3d(dst, map8, bar, x, v0, b);
+// lane 0: fetch the rows v0..v0+rows-1 of columns [x, x + box) of image b into dst (one box when no row is reflected)
+__device__ __noinline__ void issue_chunk_tma(float* dst, uint64_t* bar, const CUtensorMap* mapn, const CUtensorMap* map1, int x, int v0,
+                                             int rows, int h, int b, int sww) {
+    tma::mbar_arrive_expect_tx(bar, rows * sww * (int)sizeof(float));
+    if (v0 >= 0 && v0 + rows <= h) {
+        tma::load_3d(dst, mapn, bar, x, v0, b);
     } else {
 #pragma unroll 1
-        for (int rr = 0; rr < 8; ++rr) tma::load_3d(dst + rr * sww, map1, bar, x, reflect101(v0 + rr, h), b);
+        for (int rr = 0; rr < rows; ++rr) tma::load_3d(dst + rr * sww, map1, bar, x, reflect101(v0 + rr, h), b);
     }
 }
 
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
     extern __shared__ __align__(1024) unsigned char smem_raw[];     // TMA destinations must be 128-B aligned
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* stage = reinterpret_cast<float*>(smem_raw) + warp * C::WARP_FLOATS;   // [NS][CH][SWW]
-    float* ring = stage + C::NS * C::CH * C::SWW;                                // [RING][WC]
+    float* ring = stage + C::NS * C::SR * C::SWW;                                // [RING][WC]
     uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + C::NWARP * C::WARP_FLOATS) + warp * C::NS;
 
     const BlurArgs& a = sa.a;
@@ -279,9 +280,11 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
         tma::fence_barrier_init();
     }
     __syncwarp();
+    constexpr int HPC = C::CH / C::SR;       // staging stages (half-chunks) per chunk
+    const int n_half = n_in * HPC;
     if (lane == 0) {
-        for (int i = 0; i < C::NS && i < n_in; ++i)
-            issue_chunk_tma(stage + i * C::CH * C::SWW, &full[i], &map8, &map1, xs - C::RPAD, y0 - C::RC + i * C::CH, h, b, C::SWW);
+        for (int i = 0; i < C::NS && i < n_half; ++i)
+            issue_chunk_tma(stage + i * C::SR * C::SWW, &full[i], &map8, &map1, xs - C::RPAD, y0 - C::RC + i * C::SR, C::SR, h, b, C::SWW);
     }
 
     // row pass: lane = (row parity, column group): columns 4*cg..4*cg+3 of rows rsub, rsub+2, rsub+4, rsub+6
@@ -324,38 +327,43 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
     int phase = 0;                          // output chunk index mod RING/CH: selects the static window-load sequence
 #pragma unroll 1
     for (int i = 0; i < n_in; ++i) {
-        float* const st = stage + s * C::CH * C::SWW;
-        tma::mbar_wait(&full[s], parity);
-        if (edge) patch_reflected_columns(st, w, xs, C::RPAD, R, C::SWW, lane);
-        // ---- row pass ----
-#pragma unroll 2
-        for (int q = 0; q < 4; ++q) {
-            const int rr = rsub + 2 * q;
-            const float* srow = st + rr * C::SWW + 4 * cg;
-            float wv[C::NW];
+#pragma unroll 1
+        for (int hh = 0; hh < HPC; ++hh) {
+            float* const st = stage + s * C::SR * C::SWW;
+            tma::mbar_wait(&full[s], parity);
+            if (edge) patch_reflected_columns(st, C::SR, w, xs, C::RPAD, R, C::SWW, lane);
+            // ---- row pass of SR staged rows: lane = 4 columns x rows rsub, rsub+2 ----
 #pragma unroll
-            for (int k = 0; k < C::NW / 4; ++k) {
-                const float4 f = *reinterpret_cast<const float4*>(srow + 4 * k);
-                wv[4 * k] = f.x; wv[4 * k + 1] = f.y; wv[4 * k + 2] = f.z; wv[4 * k + 3] = f.w;
+            for (int q = 0; q < C::SR / 2; ++q) {
+                const int rr = rsub + 2 * q;
+                const float* srow = st + rr * C::SWW + 4 * cg;
+                float wv[C::NW];
+#pragma unroll
+                for (int k = 0; k < C::NW / 4; ++k) {
+                    const float4 f = *reinterpret_cast<const float4*>(srow + 4 * k);
+                    wv[4 * k] = f.x; wv[4 * k + 1] = f.y; wv[4 * k + 2] = f.z; wv[4 * k + 3] = f.w;
+                }
+                float4 o;
+                o.x = row_output<R, FMA, C::OFF + 0>(wv, taps);
+                o.y = row_output<R, FMA, C::OFF + 1>(wv, taps);
+                o.z = row_output<R, FMA, C::OFF + 2>(wv, taps);
+                o.w = row_output<R, FMA, C::OFF + 3>(wv, taps);
+                *reinterpret_cast<float4*>(ring + (wslot + hh * C::SR + rr) * C::WC + 4 * cg) = o;
             }
-            float4 o;
-            o.x = row_output<R, FMA, C::OFF + 0>(wv, taps);
-            o.y = row_output<R, FMA, C::OFF + 1>(wv, taps);
-            o.z = row_output<R, FMA, C::OFF + 2>(wv, taps);
-            o.w = row_output<R, FMA, C::OFF + 3>(wv, taps);
-            *reinterpret_cast<float4*>(ring + (wslot + rr) * C::WC + 4 * cg) = o;
+            __syncwarp();  // ring rows visible to the warp; every lane is done with stage s
+            const int hnext = i * HPC + hh + C::NS;
+            if (lane == 0 && hnext < n_half) {
+                const int v0 = y0 - C::RC + hnext * C::SR;
+                if (v0 >= 0 && v0 + C::SR <= h) {
+                    tma::mbar_arrive_expect_tx(&full[s], C::SR * C::SWW * (int)sizeof(float));
+                    tma::load_3d(st, &map8, &full[s], xs - C::RPAD, v0, b);
+                } else {
+                    issue_chunk_tma(st, &full[s], &map8, &map1, xs - C::RPAD, v0, C::SR, h, b, C::SWW);
+                }
+            }
+            if (++s == C::NS) { s = 0; parity ^= 1u; }
         }
         wslot = wslot + C::CH == C::RING ? 0 : wslot + C::CH;
-        __syncwarp();  // ring rows of chunk i visible to the warp; every lane is done with stage s
-        if (lane == 0 && i + C::NS < n_in) {
-            const int v0 = y0 - C::RC + (i + C::NS) * C::CH;
-            if (v0 >= 0 && v0 + C::CH <= h) {
-                tma::mbar_arrive_expect_tx(&full[s], C::CH * C::SWW * (int)sizeof(float));
-                tma::load_3d(st, &map8, &full[s], xs - C::RPAD, v0, b);
-            } else {
-                issue_chunk_tma(st, &full[s], &map8, &map1, xs - C::RPAD, v0, h, b, C::SWW);
-            }
-        }
         // ---- column pass for output chunk j = i - LAG ----
         const int j = i - C::LAG;
         if (j >= 0) {
@@ -413,7 +421,6 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
             }
             phase = phase + 1 == C::RING / C::CH ? 0 : phase + 1;
         }
-        if (++s == C::NS) { s = 0; parity ^= 1u; }
     }
 }
 
@@ -491,6 +498,8 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+int stream_box_rows() { return SC<5>::SR; }
 
 int stream_box_width(int r) {
     switch (r) {

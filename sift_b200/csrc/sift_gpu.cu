@@ -455,7 +455,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
         // TMA descriptors (box width depends on the blur radius); a missing descriptor only means the generic kernel runs
         auto mk = [&](CUtensorMap* m, const float* base, int w, int h, int pitch, size_t stride, int r) {
             const int bw = stream_box_width(r);
-            return bw > 0 && tma::make_image_map(&m[0], base, w, h, c->B, (size_t)pitch, stride, bw, 8) &&
+            return bw > 0 && tma::make_image_map(&m[0], base, w, h, c->B, (size_t)pitch, stride, bw, stream_box_rows()) &&
                    tma::make_image_map(&m[1], base, w, h, c->B, (size_t)pitch, stride, bw, 1);
         };
         if (c->prm.subpixel) {
@@ -1101,7 +1101,7 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
     }
     CUtensorMap map[2];
     const int bw = stream_box_width(r);
-    const bool has_map = !rc && bw > 0 && tma::make_image_map(&map[0], d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw, 8) &&
+    const bool has_map = !rc && bw > 0 && tma::make_image_map(&map[0], d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw, stream_box_rows()) &&
                          tma::make_image_map(&map[1], d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw, 1);
     if (!rc) {
         BlurArgs a{};
