@@ -74,6 +74,8 @@ struct BlurArgs {
     const int* sel_x; // decimation: destination column of source column x, or -1 (device); null = no decimation
     const int* sel_y;
     const CUtensorMap* map; // host pointer to two TMA descriptors of src (boxes stream_box_width(r) x 8 and x 1), or null
+    int z0;      // first image of the batch this launch covers (the launch's blockIdx.z counts from here)
+    int share;   // number of sibling launches expected to run concurrently (the grid is sized for 1/share of the GPU)
 };
 
 #define SIFT_CUDA_TRY(expr)                                         \
@@ -90,7 +92,7 @@ int stream_box_width(int r);   // TMA box width the streaming kernel needs for r
 int stream_box_rows();         // rows of the multi-row TMA box (the other descriptor has 1-row boxes)
 int max_generic_radius();      // largest radius the generic tile kernel can hold in shared memory
 int launch_resize_nn(const float* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int dw,
-                     int dh, const int* map_x, const int* map_y, int batch, cudaStream_t s, uint64_t* launches);
+                     int dh, const int* map_x, const int* map_y, int z0, int batch, cudaStream_t s, uint64_t* launches);
 int launch_u8_to_f32(const uint8_t* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int w,
                      int h, int batch, cudaStream_t s, uint64_t* launches);
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tile_kernel(BlurArgs a) {
     float* s_in = smem + ((2 * r + 1 + 3) & ~3);
     float* s_tmp = s_in + iw * ih;         // ih rows x kTW
 
-    const int b = blockIdx.z;
+    const int b = blockIdx.z + a.z0;
     const float* src = a.src + (size_t)b * a.src_stride;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
 
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
     uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + C::NWARP * C::WARP_FLOATS) + warp * C::NS;
 
     const BlurArgs& a = sa.a;
-    const int b = blockIdx.z;
+    const int b = blockIdx.z + a.z0;
     const int w = a.w, h = a.h;
     const int xs = (blockIdx.x * C::NWARP + warp) * C::WC;   // first column of this warp's strip
     if (xs >= w) return;                                     // warps are independent: no barrier below
@@ -459,7 +459,7 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
         }
         n_sm = cached_sm;
     }
-    const double slots = (double)n_sm * cps;
+    const double slots = (double)n_sm * cps / (a.share > 1 ? a.share : 1);
     int seg = a.h;
     double best = -1.0;
     for (int nseg = 1; nseg <= (a.h + 15) / 16; ++nseg) {
@@ -546,18 +546,18 @@ int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t
 // by the literal accumulated-double walk.
 __global__ void resize_nn_kernel(const float* __restrict__ src, size_t src_stride, int src_pitch, float* __restrict__ dst,
                                  size_t dst_stride, int dst_pitch, int dw, int dh, const int* __restrict__ map_x,
-                                 const int* __restrict__ map_y) {
+                                 const int* __restrict__ map_y, int z0) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= dw || y >= dh) return;
-    const int b = blockIdx.z;
+    const int b = blockIdx.z + z0;
     dst[(size_t)b * dst_stride + (size_t)y * dst_pitch + x] = src[(size_t)b * src_stride + (size_t)map_y[y] * src_pitch + map_x[x]];
 }
 
 int launch_resize_nn(const float* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int dw,
-                     int dh, const int* map_x, const int* map_y, int batch, cudaStream_t s, uint64_t* launches) {
+                     int dh, const int* map_x, const int* map_y, int z0, int batch, cudaStream_t s, uint64_t* launches) {
     dim3 grid((dw + 255) / 256, dh, batch);
-    resize_nn_kernel<<<grid, 256, 0, s>>>(src, src_stride, src_pitch, dst, dst_stride, dst_pitch, dw, dh, map_x, map_y);
+    resize_nn_kernel<<<grid, 256, 0, s>>>(src, src_stride, src_pitch, dst, dst_stride, dst_pitch, dw, dh, map_x, map_y, z0);
     if (launches) ++*launches;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;

@@ -190,6 +190,8 @@ struct ChunkImage {
 // One device pass in flight.
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[3]{};      // the pyramid of a pass runs as up to four image groups on stream + aux[] (tails overlap); 2 groups measured best
+    cudaEvent_t ev_fork = nullptr, ev_join[3]{};
     cudaEvent_t ev[12]{};
     // device buffers
     uint8_t* d_in_u8 = nullptr;
@@ -491,6 +493,9 @@ static int alloc_buffers(sift_gpu_ctx* c) {
     for (int si = 0; si < c->n_slots; ++si) {
         Slot& S = c->slots[si];
         CTX_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+        for (auto& st : S.aux) CTX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CTX_CUDA(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+        for (auto& e : S.ev_join) CTX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : S.ev) CTX_CUDA(cudaEventCreate(&e));
         CTX_CUDA(cudaMalloc(&S.d_in_u8, c->max_in_px * (size_t)B));
         CTX_CUDA(cudaMalloc(&S.d_in, sizeof(float) * c->max_in_px * (size_t)B));
@@ -576,44 +581,68 @@ static BlurArgs blur_args(const sift_gpu_ctx* c, const BlurSpec& b, const float*
     return a;
 }
 
-// Sift::calculate's upsample (sift.cpp:20-21) + _createDOGs (sift.cpp:381-417) for nb images in S.d_in.
-static int run_pyramid(sift_gpu_ctx* c, Slot& S, const Plan* p, const PlanSlot& ps, int nb) {
+// Sift::calculate's upsample (sift.cpp:20-21) + _createDOGs (sift.cpp:381-417) for the images [z0, z0 + cnt) of the pass.
+static int run_pyramid_group(sift_gpu_ctx* c, Slot& S, const Plan* p, const PlanSlot& ps, int z0, int cnt, int share, cudaStream_t s) {
     const int O = c->O, D = c->D;
     uint64_t* L = &S.launches;
-    cudaStream_t s = S.stream;
+    auto launch = [&](BlurArgs a) {
+        a.z0 = z0;
+        a.share = share;
+        return launch_blur(a, cnt, c->fma, s, L);
+    };
     const float* base_src = S.d_in;
     size_t base_stride = c->max_in_px;
     int base_pitch = p->in_pitch;
     if (c->prm.subpixel) {
-        CTX_TRY(launch_blur(blur_args(c, c->up_blur, S.d_in, c->max_in_px, p->in_pitch, S.d_up_tmp, c->max_in_px, p->in_pitch, nullptr, 0, 0,
-                                      p->in_w, p->in_h, ps.has_up ? ps.map_up : nullptr), nb, c->fma, s, L));
+        CTX_TRY(launch(blur_args(c, c->up_blur, S.d_in, c->max_in_px, p->in_pitch, S.d_up_tmp, c->max_in_px, p->in_pitch, nullptr, 0, 0,
+                                 p->in_w, p->in_h, ps.has_up ? ps.map_up : nullptr)));
         CTX_TRY(launch_resize_nn(S.d_up_tmp, c->max_in_px, p->in_pitch, S.d_up, c->maxP[0], p->pitch[0], p->ow[0], p->oh[0],
-                                 p->d_maps + p->up_mx, p->d_maps + p->up_my, nb, s, L));
+                                 p->d_maps + p->up_mx, p->d_maps + p->up_my, z0, cnt, s, L));
         base_src = S.d_up;
         base_stride = c->maxP[0];
         base_pitch = p->pitch[0];
     }
-    CTX_TRY(launch_blur(blur_args(c, c->base_blur, base_src, base_stride, base_pitch, S.d_gauss[0][0], c->maxP[0], p->pitch[0], nullptr, 0, 0,
-                                  p->ow[0], p->oh[0], ps.has_base ? ps.map_base : nullptr), nb, c->fma, s, L));
+    CTX_TRY(launch(blur_args(c, c->base_blur, base_src, base_stride, base_pitch, S.d_gauss[0][0], c->maxP[0], p->pitch[0], nullptr, 0, 0,
+                             p->ow[0], p->oh[0], ps.has_base ? ps.map_base : nullptr)));
     for (int o = 0; o < O; ++o) {
         for (int j = 1; j <= D; ++j)
-            CTX_TRY(launch_blur(blur_args(c, c->chain_blur[o][j], S.d_gauss[o][j - 1], c->maxP[o], p->pitch[o], S.d_gauss[o][j], c->maxP[o],
-                                          p->pitch[o], S.d_dog[o][j - 1], c->maxP[o], p->pitch[o], p->ow[o], p->oh[o],
-                                          ps.has_chain[o][j] ? ps.map_chain[o][j] : nullptr), nb, c->fma, s, L));
+            CTX_TRY(launch(blur_args(c, c->chain_blur[o][j], S.d_gauss[o][j - 1], c->maxP[o], p->pitch[o], S.d_gauss[o][j], c->maxP[o],
+                                     p->pitch[o], S.d_dog[o][j - 1], c->maxP[o], p->pitch[o], p->ow[o], p->oh[o],
+                                     ps.has_chain[o][j] ? ps.map_chain[o][j] : nullptr)));
         if (o < O - 1) {
             // alg::reduceToNextLevel: blur with the level's own label sigma, keep only the pixels the resize picks
             BlurArgs a = blur_args(c, c->reduce_blur[o], S.d_gauss[o][D - 1], c->maxP[o], p->pitch[o], S.d_gauss[o + 1][0], c->maxP[o + 1],
                                    p->pitch[o + 1], nullptr, 0, 0, p->ow[o], p->oh[o], ps.has_reduce[o] ? ps.map_reduce[o] : nullptr);
             a.sel_x = p->d_maps + p->sel_x[o];
             a.sel_y = p->d_maps + p->sel_y[o];
-            CTX_TRY(launch_blur(a, nb, c->fma, s, L));
+            CTX_TRY(launch(a));
         }
     }
     return 0;
 }
 
-// The reference's cleanup (sift.cpp:37-42): std::sort with cmpByFilter, count of leading unfiltered
-// truncated to u16.  `flags[i]` = filtered; returns the kept source indices in their new order.
+// The images of a pass are independent, so their pyramids run as up to four groups on parallel streams: while one group's
+// kernel drains its last CTAs the other groups' kernels keep the SMs busy.
+static int run_pyramid(sift_gpu_ctx* c, Slot& S, const Plan* p, const PlanSlot& ps, int nb) {
+    static const int max_groups = [] { const char* e = getenv("SIFT_GPU_PYR_GROUPS"); int g = e ? atoi(e) : 2; return g < 1 ? 1 : (g > 4 ? 4 : g); }();
+    const int groups = std::min(max_groups, nb >= 8 ? 4 : (nb >= 2 ? 2 : 1));
+    if (groups == 1) return run_pyramid_group(c, S, p, ps, 0, nb, 1, S.stream);
+    CTX_CUDA(cudaEventRecord(S.ev_fork, S.stream));
+    int z0 = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int cnt = nb / groups + (g < nb % groups ? 1 : 0);
+        cudaStream_t s = g == 0 ? S.stream : S.aux[g - 1];
+        if (g > 0) CTX_CUDA(cudaStreamWaitEvent(s, S.ev_fork, 0));
+        CTX_TRY(run_pyramid_group(c, S, p, ps, z0, cnt, groups, s));
+        if (g > 0) {
+            CTX_CUDA(cudaEventRecord(S.ev_join[g - 1], s));
+            CTX_CUDA(cudaStreamWaitEvent(S.stream, S.ev_join[g - 1], 0));
+        }
+        z0 += cnt;
+    }
+    return 0;
+}
+
 // `zero_pos`: ascending positions of the unfiltered elements of an n-element vector.  Returns the kept elements, as
 // indices into zero_pos, in their post-sort order.  The std::sort permutation is replayed by SparseFilterSort
 // (order_replay.h); the canonical mode keeps the original order (what a stable partition would do).
@@ -945,6 +974,9 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
         cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_tables);
         cudaFreeHost(S.h_keys); cudaFreeHost(S.h_key_img); cudaFreeHost(S.h_key_first); cudaFreeHost(S.h_orient); cudaFreeHost(S.h_npeaks);
         for (auto& e : S.ev) if (e) cudaEventDestroy(e);
+        for (auto& e : S.ev_join) if (e) cudaEventDestroy(e);
+        if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+        for (auto& st : S.aux) if (st) cudaStreamDestroy(st);
         if (S.stream) cudaStreamDestroy(S.stream);
     }
     for (float* b : c->desc_blocks) cudaFreeHost(b);
@@ -1124,7 +1156,7 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
                 both.insert(both.end(), my.begin(), my.end());
                 cu(cudaMalloc(&d_map, sizeof(int) * both.size()));
                 if (!rc) cu(cudaMemcpy(d_map, both.data(), sizeof(int) * both.size(), cudaMemcpyHostToDevice));
-                if (!rc) rc = launch_resize_nn(d_blur, 0, sp, d_out, 0, dp, dw, dh, d_map, d_map + dw, 1, c->slots[0].stream, nullptr);
+                if (!rc) rc = launch_resize_nn(d_blur, 0, sp, d_out, 0, dp, dw, dh, d_map, d_map + dw, 0, 1, c->slots[0].stream, nullptr);
             }
         }
     }
