@@ -238,6 +238,8 @@ def run_ours(args):
                                     [args.steps * B, acc_d["launches"], acc_d["kps"], acc_d["cands"]])
     if rank != 0:
         g.close()
+        dist.barrier()
+        dist.destroy_process_group()
         return
     wall_d, wall_h, span_d, pyr_ms, wall_u8 = mx
     images, launches, kps, cands = sm
@@ -289,6 +291,9 @@ def run_ours(args):
         line["cpu_baseline"] = None
     g.close()
     print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -138,7 +138,8 @@ struct BlurSpec {
 
 static int pitch_of(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
 
-constexpr int kSlots = 3;            // device passes in flight: stage A of pass k+1 overlaps the host replay of pass k and stage B of pass k-1
+constexpr int kSlots = 5;            // most device passes in flight (default 4, SIFT_GPU_SLOTS): stage A of later passes (upload + pyramid
+                                     // .. elimination) overlaps the host replay of pass k and stage B / download of earlier ones
 constexpr uint32_t kSurvFirst = 8192; // survivors per image copied back speculatively with the counters (the rest on demand)
 
 // The part of a plan that holds device addresses of one slot's buffers.
@@ -926,7 +927,7 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
     c->O = params->octaves; c->D = params->dogs_per_epoch; c->G = c->D + 1;
     c->fma = (params->flags & SIFT_GPU_FLAG_FMA_BLUR) != 0;
     c->B = params->max_batch;
-    c->n_slots = (params->flags & SIFT_GPU_FLAG_SERIAL) ? 1 : kSlots;
+    c->n_slots = (params->flags & SIFT_GPU_FLAG_SERIAL) ? 1 : std::min(4, kSlots);
     if (const char* e = getenv("SIFT_GPU_SLOTS")) c->n_slots = std::max(1, std::min(kSlots, atoi(e)));
     c->max_in_w = params->max_width; c->max_in_h = params->max_height;
     int rc = 0;
@@ -1039,7 +1040,7 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
     // software pipeline over the passes: A(k) is enqueued before the host replays pass k-1, whose stage B then
     // runs while A(k+1) is being enqueued and pass k-2 is collected
     const int np = (int)passes.size(), ns = c->n_slots;
-    const int lag_b = ns >= 2 ? 1 : 0, lag_f = ns >= 3 ? 2 : lag_b;
+    const int lag_b = ns >= 2 ? 1 : 0, lag_f = ns - 1;  // replay one pass behind the enqueue front, collect ns-1 behind
     for (int k = 0; k < np + lag_f; ++k) {
         if (k < np) {
             Slot& S = c->slots[k % ns];
