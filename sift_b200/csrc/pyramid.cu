@@ -15,8 +15,10 @@
 //    window (4 outputs per float4 group) into a ring of row-filtered lines, and after one
 //    __syncthreads per chunk each thread column-filters 8 rows of its own column from the ring.
 //    The main loop is unrolled over the ring period so every shared-memory address is a constant.
-//  * blur_tile_kernel: any radius / tiny images; plain shared-memory tile.
+//  * blur_strip_kernel: small levels (height <= 300), any radius: one CTA per full-height column strip.
+//  * blur_tile_kernel: any radius on large levels; plain shared-memory tile.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -100,6 +102,146 @@ int max_generic_radius() {
     int r = 1;
     while (tile_smem_bytes(r + 1) <= 227 * 1024) ++r;
     return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column-strip kernel for the small levels of the pyramid (any radius).  On a 240 x 135 or 120 x 68 level the
+// streaming kernel's segments are mostly halo and a launch is pure latency, so here one CTA takes a strip of SW
+// columns over the FULL height: no vertical halo is recomputed, the row pass of a strip is spread over all the
+// CTA's threads (K independent accumulators per thread), the reflected rows are materialised once in shared
+// memory and the column pass runs the same way.  Launch time is a few microseconds instead of 20-40.
+constexpr int kStripMaxThreads = 512;
+
+template <int SW, int K, bool FMA>
+__global__ void __launch_bounds__(kStripMaxThreads) blur_strip_kernel(BlurArgs a, int iw) {
+    extern __shared__ __align__(16) float smem[];
+    const int r = a.r, w = a.w, h = a.h, nt = 2 * r + 1;
+    float* s_taps = smem;                       // s_taps[j] multiplies source index x - r + j
+    float* s_in = smem + ((nt + 3) & ~3);       // h rows x iw: source columns x0 - r .. x0 + SW + r - 1, reflected
+    float* s_mid = s_in + h * iw;               // (h + 2r) rows x SW: row-filtered lines, rows -r .. h + r - 1
+
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int b = blockIdx.z + a.z0;
+    const int x0 = blockIdx.x * SW;
+    const float* src = a.src + (size_t)b * a.src_stride;
+
+    for (int i = tid; i < nt; i += T) s_taps[i] = a.taps[nt - 1 - i];
+    {
+        // eight rows per thread in flight: the level was just written by the previous launch, so this is L2 latency
+        const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5, span = SW + 2 * r;
+        constexpr int U = 8;
+        for (int tx = lane; tx < span; tx += 32) {
+            const float* colp = src + reflect101(x0 - r + tx, w);
+            for (int y = warp; y < h; y += U * nwarp) {
+                float v[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) v[q] = colp[(size_t)min(y + q * nwarp, h - 1) * a.src_pitch];
+#pragma unroll
+                for (int q = 0; q < U; ++q)
+                    if (y + q * nwarp < h) s_in[(y + q * nwarp) * iw + tx] = v[q];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int col = tid % SW, rg = tid / SW, rs = T / SW;  // thread = column `col`, rows rg, rg + rs, rg + 2 rs, ...
+    for (int row0 = rg; row0 < h; row0 += K * rs) {
+        const float* p[K];
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int y = min(row0 + k * rs, h - 1);
+            p[k] = s_in + y * iw + col;
+            acc[k] = 0.0f;
+        }
+#pragma unroll 4
+        for (int j = 0; j < nt; ++j) {
+            const float t = s_taps[j];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = tap_acc<FMA>(acc[k], t, p[k][j]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int y = row0 + k * rs;
+            if (y < h) s_mid[(y + r) * SW + col] = acc[k];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * r * SW; i += T) {
+        const int q = i / SW, c = i % SW;
+        const int yy = q < r ? q - r : h + (q - r);
+        s_mid[(yy + r) * SW + c] = s_mid[(reflect101(yy, h) + r) * SW + c];
+    }
+    __syncthreads();
+
+    const int gx = x0 + col;
+    for (int row0 = rg; row0 < h; row0 += K * rs) {
+        const float* p[K];
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int y = min(row0 + k * rs, h - 1);
+            p[k] = s_mid + y * SW + col;  // rows y .. y + 2r of s_mid are source rows y - r .. y + r
+            acc[k] = 0.0f;
+        }
+#pragma unroll 4
+        for (int j = 0; j < nt; ++j) {
+            const float t = s_taps[j];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = tap_acc<FMA>(acc[k], t, p[k][j * SW]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int y = row0 + k * rs;
+            if (y < h && gx < w) store_out(a, b, gx, y, acc[k], s_in[y * iw + r + col]);
+        }
+    }
+}
+
+static int strip_iw(int sw, int r) {
+    int iw = sw + 2 * r;
+    if (sw == 16) while (iw % 32 != 16) ++iw;  // two rows per warp: keep them on disjoint banks
+    return iw;
+}
+
+static size_t strip_smem_bytes(int sw, int r, int h) {
+    return sizeof(float) * (size_t)(((2 * r + 1 + 3) & ~3) + h * strip_iw(sw, r) + (h + 2 * r) * sw);
+}
+
+static int strip_max_height() {
+    static const int v = [] { const char* e = getenv("SIFT_GPU_STRIP_MAX_H"); return e ? atoi(e) : 300; }();
+    return v;
+}
+
+template <int SW, int K>
+static int launch_strip_k(const BlurArgs& a, int batch, bool fma, int threads, size_t smem, cudaStream_t s) {
+    dim3 grid((a.w + SW - 1) / SW, 1, batch);
+    const int iw = strip_iw(SW, a.r);
+    static bool attr[2] = {false, false};
+    if (!attr[fma ? 1 : 0]) {
+        if (fma) SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        else SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr[fma ? 1 : 0] = true;
+    }
+    if (fma) blur_strip_kernel<SW, K, true><<<grid, threads, smem, s>>>(a, iw);
+    else blur_strip_kernel<SW, K, false><<<grid, threads, smem, s>>>(a, iw);
+    SIFT_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// returns -1 when the level does not qualify
+static int launch_strip(const BlurArgs& a, int batch, bool fma, cudaStream_t s) {
+    if (a.h > strip_max_height() || a.r >= a.h || a.r >= a.w) return -1;
+    const size_t cap = 200 * 1024;
+    int sw = 32;
+    if (strip_smem_bytes(32, a.r, a.h) > cap || ((a.w + 31) / 32) * batch < 120) sw = 16;
+    const size_t smem = strip_smem_bytes(sw, a.r, a.h);
+    if (smem > cap) return -1;
+    const int threads = a.h * sw >= 4096 ? 512 : 256;
+    const int per_thread = (a.h + threads / sw - 1) / (threads / sw);     // row slots of one thread
+    const bool k8 = (per_thread + 7) / 8 * 8 <= (per_thread + 3) / 4 * 4;  // K = 8 unless it wastes more slots than K = 4
+    if (sw == 32) return k8 ? launch_strip_k<32, 8>(a, batch, fma, threads, smem, s) : launch_strip_k<32, 4>(a, batch, fma, threads, smem, s);
+    return k8 ? launch_strip_k<16, 8>(a, batch, fma, threads, smem, s) : launch_strip_k<16, 4>(a, batch, fma, threads, smem, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -515,6 +657,10 @@ int stream_box_width(int r) {
 
 int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t* launches) {
     if (launches) ++*launches;
+    {
+        const int rc = launch_strip(a, batch, fma, s);
+        if (rc >= 0) return rc;
+    }
     if (a.map && a.taps_host && a.w >= 32 && a.h >= 16) {
         switch (a.r) {
             case 3: return launch_stream_r<3>(a, batch, fma, s);
