@@ -138,7 +138,7 @@ struct BlurSpec {
 
 static int pitch_of(int w) { return (w + kPitchAlign - 1) / kPitchAlign * kPitchAlign; }
 
-constexpr int kSlots = 5;            // most device passes in flight (default 4, SIFT_GPU_SLOTS): stage A of later passes (upload + pyramid
+constexpr int kSlots = 6;            // most device passes in flight (default 5, SIFT_GPU_SLOTS): stage A of later passes (upload + pyramid
                                      // .. elimination) overlaps the host replay of pass k and stage B / download of earlier ones
 constexpr uint32_t kSurvFirst = 8192; // survivors per image copied back speculatively with the counters (the rest on demand)
 
@@ -571,6 +571,18 @@ static float* take_desc_block(sift_gpu_ctx* c, size_t floats) {
 }
 
 // ---- device passes ------------------------------------------------------------------------------
+__global__ void fetch_keys_kernel(const uint2* __restrict__ h_keys, uint2* __restrict__ d_keys, const uint32_t* __restrict__ h_img,
+                                  uint32_t* __restrict__ d_img, const uint32_t* __restrict__ h_first, uint32_t* __restrict__ d_first,
+                                  uint32_t n_keys, uint32_t n_first) {
+    static_assert(sizeof(KeyIn) == sizeof(uint2), "KeyIn is copied as uint2");
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_keys; i += stride) {
+        d_keys[i] = h_keys[i];
+        d_img[i] = h_img[i];
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_first; i += stride) d_first[i] = h_first[i];
+}
+
 static BlurArgs blur_args(const sift_gpu_ctx* c, const BlurSpec& b, const float* src, size_t sstride, int spitch, float* dst, size_t dstride,
                           int dpitch, float* dog, size_t gstride, int gpitch, int w, int h, const CUtensorMap* map) {
     BlurArgs a{};
@@ -713,6 +725,7 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
     }
 }
 
+static double g_trace[8];  // SIFT_GPU_TRACE: host wall time per phase of the pass loop (diagnostics only)
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -768,7 +781,9 @@ static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) 
     const int nb = (int)S.imgs.size();
     cudaStream_t s = S.stream;
     uint64_t* L = &S.launches;
+    const double t_w0 = now_ms();
     CTX_CUDA(cudaEventSynchronize(S.ev[5]));
+    g_trace[1] += now_ms() - t_w0;
     // images with more survivors than the speculative copy holds fetch the remainder now (rare)
     for (int b = 0; b < nb; ++b) {
         S.surv_overflow[(size_t)b].clear();
@@ -803,14 +818,20 @@ static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) 
         std::fill(S.h_key_img + off, S.h_key_img + off + S.rep[(size_t)b].keys.size(), (uint32_t)b);
     }
     c->tm.host_order_ms += (float)(now_ms() - t_host0);
+    g_trace[2] += now_ms() - t_host0;
+    const double t_e0 = now_ms();
 
     CTX_CUDA(cudaEventRecord(S.ev[6], s));
     S.h_desc = take_desc_block(c, n_keys * kDescLen);
     if (!S.h_desc) return set_error(c, SIFT_GPU_E_CUDA, "pinned descriptor block allocation failed");
     if (n_keys) {
-        CTX_CUDA(cudaMemcpyAsync(S.d_keys, S.h_keys, sizeof(KeyIn) * n_keys, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(cudaMemcpyAsync(S.d_key_img, S.h_key_img, sizeof(uint32_t) * n_keys, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(cudaMemcpyAsync(S.d_key_first, S.h_key_first, sizeof(uint32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, s));
+        // the key lists are pulled out of pinned host memory by a kernel: a cudaMemcpyAsync would queue on the
+        // host-to-device copy engine behind the frame uploads of the next passes (several milliseconds)
+        const int blocks = (int)std::min<size_t>(64, (n_keys + 255) / 256);
+        fetch_keys_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint2*>(S.h_keys), reinterpret_cast<uint2*>(S.d_keys), S.h_key_img,
+                                                  S.d_key_img, S.h_key_first, S.d_key_first, (uint32_t)n_keys, (uint32_t)(nb + 1));
+        ++*L;
+        CTX_CUDA(cudaGetLastError());
     }
     CTX_CUDA(cudaEventRecord(S.ev[7], s));
     const int n_targets = (int)ps.targets_host.size();
@@ -837,6 +858,7 @@ static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) 
         CTX_CUDA(cudaMemcpyAsync(S.h_desc, S.d_desc, sizeof(float) * kDescLen * n_keys, cudaMemcpyDeviceToHost, s));
     }
     CTX_CUDA(cudaEventRecord(S.ev[10], s));
+    g_trace[3] += now_ms() - t_e0;
     return 0;
 }
 
@@ -844,7 +866,10 @@ static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) 
 static int finish_pass(sift_gpu_ctx* c, Slot& S, sift_gpu_result* results) {
     Plan* p = S.plan;
     const int nb = (int)S.imgs.size();
+    const double t_w0 = now_ms();
     CTX_CUDA(cudaEventSynchronize(S.ev[10]));
+    g_trace[4] += now_ms() - t_w0;
+    const double t_f0 = now_ms();
     for (int b = 0; b < nb; ++b) {
         const int ri = S.imgs[(size_t)b].result_index;
         sift_gpu_result& R = results[ri];
@@ -896,7 +921,14 @@ static int finish_pass(sift_gpu_ctx* c, Slot& S, sift_gpu_result* results) {
     c->tm.descriptor_ms += el(8, 9);
     c->tm.d2h_results_ms += el(9, 10);
     c->tm.kernel_launches += S.launches;
+    if (getenv("SIFT_GPU_TRACE")) {
+        float t[11];
+        for (int i = 0; i < 11; ++i) cudaEventElapsedTime(&t[i], c->ev_first, S.ev[i]);
+        fprintf(stderr, "[sift_gpu pass] h2d %.3f-%.3f pyr -%.3f ext -%.3f elim -%.3f d2h -%.3f | keys %.3f-%.3f ori -%.3f desc -%.3f d2h -%.3f\n", t[0], t[1],
+                t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], t[10]);
+    }
     S.busy = false;
+    g_trace[5] += now_ms() - t_f0;
     return 0;
 }
 
@@ -927,7 +959,7 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
     c->O = params->octaves; c->D = params->dogs_per_epoch; c->G = c->D + 1;
     c->fma = (params->flags & SIFT_GPU_FLAG_FMA_BLUR) != 0;
     c->B = params->max_batch;
-    c->n_slots = (params->flags & SIFT_GPU_FLAG_SERIAL) ? 1 : std::min(4, kSlots);
+    c->n_slots = (params->flags & SIFT_GPU_FLAG_SERIAL) ? 1 : std::min(5, kSlots);
     if (const char* e = getenv("SIFT_GPU_SLOTS")) c->n_slots = std::max(1, std::min(kSlots, atoi(e)));
     c->max_in_w = params->max_width; c->max_in_h = params->max_height;
     int rc = 0;
@@ -1040,7 +1072,11 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
     // software pipeline over the passes: A(k) is enqueued before the host replays pass k-1, whose stage B then
     // runs while A(k+1) is being enqueued and pass k-2 is collected
     const int np = (int)passes.size(), ns = c->n_slots;
-    const int lag_b = ns >= 2 ? 1 : 0, lag_f = ns - 1;  // replay one pass behind the enqueue front, collect ns-1 behind
+    // the host replays pass k - lag_b while stage A of passes up to k is queued on the device (queueing ahead keeps the
+    // device fed while the host waits for a stage A to end), and collects ns-1 passes behind the enqueue front
+    int lag_b = ns >= 4 ? ns - 2 : (ns >= 2 ? 1 : 0);
+    if (const char* e = getenv("SIFT_GPU_LAG")) lag_b = std::max(ns >= 2 ? 1 : 0, std::min(ns - 1, atoi(e)));
+    const int lag_f = ns - 1;
     for (int k = 0; k < np + lag_f; ++k) {
         if (k < np) {
             Slot& S = c->slots[k % ns];
@@ -1048,7 +1084,9 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
             S.imgs = passes[(size_t)k].imgs;
             S.busy = true;
             if (k == 0) CTX_CUDA(cudaEventRecord(c->ev_first, S.stream));
+            const double t_a0 = now_ms();
             CTX_TRY(enqueue_stage_a(c, S, k % ns));
+            g_trace[0] += now_ms() - t_a0;
         }
         const int kb = k - lag_b;
         if (kb >= 0 && kb < np) CTX_TRY(replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
@@ -1074,6 +1112,11 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
     c->tm.device_total_ms = c->tm.h2d_ms + c->tm.pyramid_ms + c->tm.extrema_ms + c->tm.eliminate_ms + c->tm.d2h_survivors_ms +
                             c->tm.h2d_keypoints_ms + c->tm.orientation_ms + c->tm.descriptor_ms + c->tm.d2h_results_ms;
     c->tm.wall_ms = (float)(now_ms() - t0);
+    if (getenv("SIFT_GPU_TRACE")) {
+        fprintf(stderr, "[sift_gpu trace] %d passes, wall %.2f ms: enqueueA %.2f  waitA %.2f  replay %.2f  enqueueB %.2f  waitC %.2f  collect %.2f\n", np,
+                c->tm.wall_ms, g_trace[0], g_trace[1], g_trace[2], g_trace[3], g_trace[4], g_trace[5]);
+    }
+    for (double& v : g_trace) v = 0.0;
     return first_error;
 }
 
