@@ -7,14 +7,12 @@
 // (SURVEY A.2).  Compiled with -fmad=false: the exact path is mul-then-add like the reference's
 // mulss/addss, the FMA path asks for fmaf explicitly.
 //
-// Two implementations:
-//  * blur_stream_kernel<R>: the hot one.  A CTA owns a 256-column strip of a row segment and marches
-//    down it in chunks of 8 rows.  Input rows are staged in shared memory by TMA (3-D tensor map
-//    x, y, image; out-of-bounds zero fill, then a reflect patch on edge strips), one warp per row:
-//    the warp's leader issues the row's boxes, the warp row-filters it with a register-blocked
-//    window (4 outputs per float4 group) into a ring of row-filtered lines, and after one
-//    __syncthreads per chunk each thread column-filters 8 rows of its own column from the ring.
-//    The main loop is unrolled over the ring period so every shared-memory address is a constant.
+// Three implementations (launch_blur picks):
+//  * blur_stream_kernel<R>: the hot one (radii 3, 5, 7, 10, 14, 19 on levels taller than 300 rows).
+//    Every warp is an independent pipeline over a 64-column strip of a row segment: TMA stages 8-row
+//    boxes (3-D tensor map x, y, image; out-of-bounds zero fill, then a reflect patch on edge strips),
+//    the warp row-filters them into its private ring of row-filtered lines and column-filters from the
+//    ring; DoG and decimation are fused into the epilogue.  No CTA-wide barrier.
 //  * blur_strip_kernel: small levels (height <= 300), any radius: one CTA per full-height column strip.
 //  * blur_tile_kernel: any radius on large levels; plain shared-memory tile.
 #include <cmath>
