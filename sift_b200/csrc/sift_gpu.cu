@@ -181,6 +181,11 @@ struct ReplayOut {
     std::vector<sift_gpu_keypoint> kps;  // final vector order (orientation/descriptor filled later)
     std::vector<KeyIn> keys;             // the subset that goes to the device, same order
     std::vector<uint32_t> key_of;        // kp -> index in keys or ~0u
+    // kept for the rare pass that has to be redone because a keypoint came back with several orientations
+    std::vector<Surv> l1;                // the points after the first cleanup, vector order
+    std::vector<uint32_t> inside;        // positions in l1 that pass the orientation-stage bounds test
+    std::vector<uint32_t> kp_l1;         // kp -> position in l1
+    bool truncated = false;              // the u16 size of the second cleanup dropped points
 };
 
 struct ChunkImage {
@@ -670,6 +675,22 @@ static void cleanup_order(uint32_t n, const std::vector<uint32_t>& zero_pos, boo
     kept->resize((uint16_t)zero_pos.size());  // u16_t size = distance(begin, first filtered) (sift.cpp:41)
 }
 
+// Fills the result record of a point that reached _createDecriptors; returns whether it gets a descriptor.
+static bool make_keypoint(const sift_gpu_ctx* c, const Plan* p, const Surv& s, sift_gpu_keypoint* k, KeyIn* ki) {
+    const int slot = p->class_target[(size_t)(s.octave * c->D + s.index)];
+    const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
+    k->x = s.x; k->y = s.y; k->octave = s.octave; k->index = s.index;
+    k->scale = c->d_scale[s.octave][s.index];
+    k->orientation = 0.0f;
+    k->reserved = 0;
+    // _createDecriptors bounds test (sift.cpp:65-70)
+    const bool reject = s.x < kRegion || s.x > tw - kRegion || s.y < kRegion || s.y > th - kRegion;
+    k->filtered = reject ? 1 : 0;
+    k->desc_len = reject ? 0 : kDescLen;
+    ki->x = s.x; ki->y = s.y; ki->octave = s.octave; ki->index = s.index; ki->tgt = (uint8_t)slot; ki->pad = 0;
+    return !reject;
+}
+
 // Host half of Sift::calculate between _eliminateEdgeResponses and _createDecriptors (sift.cpp:37-55).
 static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, const Surv* surv_in, uint32_t n_surv,
                          ReplayOut* out) {
@@ -700,29 +721,22 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
     }
     std::vector<uint32_t> L2;  // indices into `inside`
     cleanup_order((uint32_t)L1.size(), inside, canonical, &L2);
+    out->truncated = L2.size() != inside.size();
+    out->l1.resize(L1.size());
+    for (size_t i = 0; i < L1.size(); ++i) out->l1[i] = S[L1[i]];
     out->kps.resize(L2.size());
     out->key_of.assign(L2.size(), ~0u);
+    out->kp_l1.resize(L2.size());
     out->keys.clear();
     for (size_t i = 0; i < L2.size(); ++i) {
-        const Surv& s = S[L1[inside[L2[i]]]];
-        const int slot = p->class_target[(size_t)(s.octave * D + s.index)];
-        const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
-        sift_gpu_keypoint& k = out->kps[i];
-        k.x = s.x; k.y = s.y; k.octave = s.octave; k.index = s.index;
-        k.scale = c->d_scale[s.octave][s.index];
-        k.orientation = 0.0f;
-        k.reserved = 0;
-        // _createDecriptors bounds test (sift.cpp:65-70)
-        const bool reject = s.x < kRegion || s.x > tw - kRegion || s.y < kRegion || s.y > th - kRegion;
-        k.filtered = reject ? 1 : 0;
-        k.desc_len = reject ? 0 : kDescLen;
-        if (!reject) {
+        out->kp_l1[i] = inside[L2[i]];
+        KeyIn ki;
+        if (make_keypoint(c, p, out->l1[inside[L2[i]]], &out->kps[i], &ki)) {
             out->key_of[i] = (uint32_t)out->keys.size();
-            KeyIn ki;
-            ki.x = s.x; ki.y = s.y; ki.octave = s.octave; ki.index = s.index; ki.tgt = (uint8_t)slot; ki.pad = 0;
             out->keys.push_back(ki);
         }
     }
+    out->inside.swap(inside);
 }
 
 static double g_trace[8];  // SIFT_GPU_TRACE: host wall time per phase of the pass loop (diagnostics only)
@@ -862,14 +876,115 @@ static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) 
     return 0;
 }
 
+// Rare path (sift.cpp:194-200): some keypoint of the pass came back with more than one orientation peak.  The
+// reference then appends one copy of the point per peak (`peaks.begin()++` is begin(): the first peak is copied
+// too) behind all the points, which changes what the second cleanup sort sees and therefore the order the
+// descriptors are built in.  The pass's host replay is redone from the first cleanup on with the peaks known, and
+// the descriptors are recomputed for the new key list with the orientations supplied by the host.  Synchronous.
+static int redo_with_extra_orientations(sift_gpu_ctx* c, Slot& S, int slot_index) {
+    Plan* p = S.plan;
+    const PlanSlot& ps = p->ps[slot_index];
+    const int nb = (int)S.imgs.size();
+    const bool canonical = (c->prm.flags & SIFT_GPU_FLAG_ORDER_CANONICAL) != 0;
+    cudaStream_t s = S.stream;
+    std::vector<float> peaks(S.n_keys * 36);
+    CTX_CUDA(cudaMemcpy(peaks.data(), S.d_peaks, sizeof(float) * peaks.size(), cudaMemcpyDeviceToHost));
+    std::vector<std::vector<float>> new_orient((size_t)nb);
+    for (int b = 0; b < nb; ++b) {
+        ReplayOut& ro = S.rep[(size_t)b];
+        if (ro.status != SIFT_GPU_OK) continue;
+        if (ro.truncated) {  // orientations of the dropped points were never computed
+            ro.status = SIFT_GPU_E_UNSUPPORTED;
+            c->error = "more than 65535 keypoints together with extra orientation peaks: not supported";
+            continue;
+        }
+        const size_t off = S.h_key_first[b];
+        std::vector<int64_t> key_of_l1(ro.l1.size(), -1);
+        for (size_t i = 0; i < ro.kps.size(); ++i)
+            if (ro.key_of[i] != ~0u) key_of_l1[ro.kp_l1[i]] = (int64_t)(off + ro.key_of[i]);
+        // the vector as _orientationAssignment leaves it: every point of l1 (filtered unless inside), then the copies
+        struct Entry { uint32_t l1; float orientation; };
+        std::vector<Entry> V(ro.l1.size());
+        std::vector<uint32_t> zero_pos;
+        for (size_t q = 0; q < ro.l1.size(); ++q) V[q] = Entry{(uint32_t)q, 0.0f};
+        for (uint32_t q : ro.inside) {
+            zero_pos.push_back(q);
+            V[q].orientation = S.h_orient[key_of_l1[q]];
+        }
+        for (uint32_t q : ro.inside) {
+            const size_t k = (size_t)key_of_l1[q];
+            const uint32_t np = S.h_npeaks[k];
+            if (np <= 1) continue;
+            for (uint32_t j = 0; j < np; ++j) {
+                zero_pos.push_back((uint32_t)V.size());
+                V.push_back(Entry{q, peaks[k * 36 + j]});
+            }
+        }
+        std::vector<uint32_t> kept;
+        cleanup_order((uint32_t)V.size(), zero_pos, canonical, &kept);
+        ReplayOut nr;
+        nr.n_survivors = ro.n_survivors;
+        nr.kps.resize(kept.size());
+        nr.key_of.assign(kept.size(), ~0u);
+        for (size_t i = 0; i < kept.size(); ++i) {
+            const Entry& e = V[zero_pos[kept[i]]];
+            KeyIn ki;
+            if (make_keypoint(c, p, ro.l1[e.l1], &nr.kps[i], &ki)) {
+                nr.key_of[i] = (uint32_t)nr.keys.size();
+                nr.keys.push_back(ki);
+                new_orient[(size_t)b].push_back(e.orientation);
+            }
+            nr.kps[i].orientation = e.orientation;
+        }
+        ro.kps.swap(nr.kps);
+        ro.key_of.swap(nr.key_of);
+        ro.keys.swap(nr.keys);
+    }
+    size_t n_keys = 0;
+    for (int b = 0; b < nb; ++b) {
+        S.h_key_first[b] = (uint32_t)n_keys;
+        if (S.rep[(size_t)b].status == SIFT_GPU_OK) n_keys += S.rep[(size_t)b].keys.size();
+    }
+    S.h_key_first[nb] = (uint32_t)n_keys;
+    S.n_keys = n_keys;
+    CTX_TRY(ensure_key_capacity(c, S, n_keys));
+    for (int b = 0; b < nb; ++b) {
+        const ReplayOut& ro = S.rep[(size_t)b];
+        if (ro.status != SIFT_GPU_OK) continue;
+        const size_t off = S.h_key_first[b];
+        std::copy(ro.keys.begin(), ro.keys.end(), S.h_keys + off);
+        std::fill(S.h_key_img + off, S.h_key_img + off + ro.keys.size(), (uint32_t)b);
+        std::copy(new_orient[(size_t)b].begin(), new_orient[(size_t)b].end(), S.h_orient + off);
+        std::fill(S.h_npeaks + off, S.h_npeaks + off + ro.keys.size(), 1u);
+    }
+    S.h_desc = take_desc_block(c, n_keys * kDescLen);
+    if (!S.h_desc) return set_error(c, SIFT_GPU_E_CUDA, "pinned descriptor block allocation failed");
+    if (n_keys) {
+        CTX_CUDA(cudaMemcpyAsync(S.d_keys, S.h_keys, sizeof(KeyIn) * n_keys, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(S.d_key_img, S.h_key_img, sizeof(uint32_t) * n_keys, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(S.d_key_first, S.h_key_first, sizeof(uint32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, s));
+        CTX_CUDA(cudaMemcpyAsync(S.d_orient, S.h_orient, sizeof(float) * n_keys, cudaMemcpyHostToDevice, s));
+        CTX_TRY(launch_descriptors(ps.targets_dev, (int)ps.targets_host.size(), S.d_tables, S.d_keys, S.d_key_img, S.d_key_first, (uint32_t)n_keys,
+                                   S.d_orient, S.d_desc, s, &S.launches));
+        CTX_CUDA(cudaMemcpyAsync(S.h_desc, S.d_desc, sizeof(float) * kDescLen * n_keys, cudaMemcpyDeviceToHost, s));
+    }
+    CTX_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 // Waits for stage B of the pass in `S` and fills the caller's results.
-static int finish_pass(sift_gpu_ctx* c, Slot& S, sift_gpu_result* results) {
+static int finish_pass(sift_gpu_ctx* c, Slot& S, int slot_index, sift_gpu_result* results) {
     Plan* p = S.plan;
     const int nb = (int)S.imgs.size();
     const double t_w0 = now_ms();
     CTX_CUDA(cudaEventSynchronize(S.ev[10]));
     g_trace[4] += now_ms() - t_w0;
     const double t_f0 = now_ms();
+    {
+        bool extra = false;
+        for (size_t k = 0; k < S.n_keys && !extra; ++k) extra = S.h_npeaks[k] > 1;
+        if (extra) CTX_TRY(redo_with_extra_orientations(c, S, slot_index));
+    }
     for (int b = 0; b < nb; ++b) {
         const int ri = S.imgs[(size_t)b].result_index;
         sift_gpu_result& R = results[ri];
@@ -888,7 +1003,6 @@ static int finish_pass(sift_gpu_ctx* c, Slot& S, sift_gpu_result* results) {
         for (size_t i = 0; i < ro.kps.size(); ++i) {
             const uint32_t ko = ro.key_of[i];
             if (ko == ~0u) { all = false; continue; }
-            if (S.h_npeaks[off + ko] > 1) R.status = SIFT_GPU_E_UNSUPPORTED;  // extra orientations (sift.cpp:194-200)
             ro.kps[i].orientation = S.h_orient[off + ko];
         }
         HO.kps.swap(ro.kps);
@@ -905,8 +1019,6 @@ static int finish_pass(sift_gpu_ctx* c, Slot& S, sift_gpu_result* results) {
             }
             R.desc = blk;
         }
-        if (R.status == SIFT_GPU_E_UNSUPPORTED)
-            c->error = "a keypoint produced more than one orientation peak (sift.cpp:194-200): not supported yet";
     }
     // stage times of this pass (device time of each stage; passes overlap, so their sum can exceed span_ms)
     float ms = 0.0f;
@@ -1094,7 +1206,7 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
         if (kf >= 0 && kf < np) {
             Slot& S = c->slots[kf % ns];
             if (kf == np - 1) CTX_CUDA(cudaEventRecord(c->ev_last, S.stream));
-            CTX_TRY(finish_pass(c, S, results));
+            CTX_TRY(finish_pass(c, S, kf % ns, results));
             c->last_slot = kf % ns;
             for (const ChunkImage& ci : S.imgs)
                 if (results[ci.result_index].status != SIFT_GPU_OK && !first_error) {

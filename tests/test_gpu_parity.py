@@ -57,6 +57,32 @@ def test_small_synthetic_bit_exact(built, w, h, octaves, seed):
     full_compare(synth_frame(w, h, seed), octaves, batch=2)
 
 
+@pytest.mark.parametrize("offset,seed,w,h", [(300.0, 1, 200, 150), (120.0, 1, 200, 150), (140.0, 3, 320, 240)])
+def test_extra_orientation_peaks(built, offset, seed, w, h):
+    """sift.cpp:194-200: a keypoint with several orientation peaks is appended once per peak (the first one too).
+    Unreachable for non-negative images (every sample falls into bin 0 and the bin sum is positive), but a float
+    image with negative grey values makes the bin sum negative and the histogram grows two peaks."""
+    img = synth_frame(w, h, seed) - np.float32(offset)
+    kp = full_compare(img, 3, batch=2)
+    plain = ol.Oracle(3, 3, 1.6, K, False).calculate(synth_frame(w, h, seed))
+    assert kp["x"].size > plain["x"].size and np.unique(kp["orientation"]).size > 2
+
+
+def test_extra_orientation_peaks_mixed_batch(built):
+    """Only one image of the pass takes the redo path; its neighbours must come out unchanged."""
+    a, b = synth_frame(200, 150, 1), synth_frame(200, 150, 1) - np.float32(300)
+    g = capi.SiftGpu(3, 3, 1.6, K, False, max_width=200, max_height=150, max_batch=4)
+    res = g.run([a, b, a, b])
+    ref = [ol.Oracle(3, 3, 1.6, K, False).calculate(x) for x in (a, b)]
+    for i, r in enumerate(res):
+        okp = ref[i % 2]
+        assert r["status"] == 0 and r["kps"].size == okp["x"].size
+        for f in ("x", "y", "octave", "index", "scale", "orientation", "filtered"):
+            assert np.array_equal(r["kps"][f], okp[f], equal_nan=f == "orientation"), f
+        assert np.array_equal(r["desc"], okp["desc"])
+    g.close()
+
+
 def test_config1_parrot_defaults(built, parrot):
     """BASELINE config 1: example/parrot.jpg band 0, sigma 1.6, k sqrt2, 4 octaves, 3 DoGs, subpixel 0."""
     kp = full_compare(parrot, 4)
