@@ -56,6 +56,8 @@ struct ScanLayer {
     int n_yw;            // ceil(h/32) mask words per column
     uint32_t mask_off;   // word offset of this layer inside one image's mask block
     uint32_t col_base;   // first global column id of this layer
+    uint32_t tile_base;  // first CTA of this layer in the single mask launch (set_scan_tiles)
+    uint32_t tiles_x;    // CTAs per row-block: ceil(w / 128)
     uint8_t octave, index;
 };
 
@@ -96,8 +98,11 @@ int launch_resize_nn(const float* src, size_t src_stride, int src_pitch, float* 
 int launch_u8_to_f32(const uint8_t* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int w,
                      int h, int batch, cudaStream_t s, uint64_t* launches);
 
+// fills tile_base / tiles_x of a layer list (call before the list is copied to the device)
+void set_scan_tiles(ScanLayer* layers, int n_layers);
+// pass_mask: second bit plane (candidates that also pass the cheap elimination tests), or null to leave every candidate unfiltered
 int launch_extrema(const ScanLayer* layers_dev, const ScanLayer* layers_host, int n_layers, int total_cols,
-                   uint32_t mask_words_per_image, uint32_t* mask, uint32_t* col_count, uint32_t* col_off,
+                   uint32_t mask_words_per_image, uint32_t* mask, uint32_t* pass_mask, uint32_t* col_count, uint32_t* col_off,
                    Cand* cands, size_t cand_stride, uint32_t* n_cand, int batch, cudaStream_t s, uint64_t* launches);
 
 int launch_eliminate(const ScanLayer* layers_dev, int n_layers, Cand* cands, size_t cand_stride,

@@ -26,8 +26,8 @@ __global__ void __launch_bounds__(128) eliminate_kernel(const ScanLayer* __restr
         const uint32_t i = base + threadIdx.x;
         bool keep = false;
         Cand c;
-        if (i < n) {
-            c = cl[i];
+        if (i < n) c = cl[i];
+        if (i < n && !c.filtered) {  // the extrema kernels already applied the det / edge-ratio tests (extrema.cu, PREFILTER)
             const ScanLayer L = layers[c.octave * mid_layers + (c.index - 1)];
             const size_t off = (size_t)b * L.stride;
             const float* D0 = L.d0 + off;

@@ -105,105 +105,120 @@ int max_generic_radius() {
 // ---------------------------------------------------------------------------------------------
 // Column-strip kernel for the small levels of the pyramid (any radius).  On a 240 x 135 or 120 x 68 level the
 // streaming kernel's segments are mostly halo and a launch is pure latency, so here one CTA takes a strip of SW
-// columns over the FULL height: no vertical halo is recomputed, the row pass of a strip is spread over all the
-// CTA's threads (K independent accumulators per thread), the reflected rows are materialised once in shared
-// memory and the column pass runs the same way.  Launch time is a few microseconds instead of 20-40.
+// columns over the FULL height: no vertical halo is recomputed and both passes are spread over all the CTA's
+// threads.  Each thread produces 4 adjacent outputs (row pass: 4 columns of a row, column pass: 4 rows of a
+// column) and walks the taps in groups of 4 with a sliding register window, so one shared-memory value feeds
+// 4 multiply-adds (1 B of shared-memory traffic per tap instead of 4).  The radius is a run-time value: the tap
+// list is padded with zeros to a multiple of 4 at both ends, which leaves every partial sum unchanged
+// (acc + 0*v == acc for the finite grey values of an image; the padded window only touches real pixels).
 constexpr int kStripMaxThreads = 512;
 
-template <int SW, int K, bool FMA>
-__global__ void __launch_bounds__(kStripMaxThreads) blur_strip_kernel(BlurArgs a, int iw) {
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <bool FMA>
+__device__ __forceinline__ void window4(float& o0, float& o1, float& o2, float& o3, const float4 t, const float a0, const float a1,
+                                        const float a2, const float a3, const float b0, const float b1, const float b2) {
+    o0 = tap_acc<FMA>(o0, t.x, a0); o0 = tap_acc<FMA>(o0, t.y, a1); o0 = tap_acc<FMA>(o0, t.z, a2); o0 = tap_acc<FMA>(o0, t.w, a3);
+    o1 = tap_acc<FMA>(o1, t.x, a1); o1 = tap_acc<FMA>(o1, t.y, a2); o1 = tap_acc<FMA>(o1, t.z, a3); o1 = tap_acc<FMA>(o1, t.w, b0);
+    o2 = tap_acc<FMA>(o2, t.x, a2); o2 = tap_acc<FMA>(o2, t.y, a3); o2 = tap_acc<FMA>(o2, t.z, b0); o2 = tap_acc<FMA>(o2, t.w, b1);
+    o3 = tap_acc<FMA>(o3, t.x, a3); o3 = tap_acc<FMA>(o3, t.y, b0); o3 = tap_acc<FMA>(o3, t.z, b1); o3 = tap_acc<FMA>(o3, t.w, b2);
+}
+
+// Shared-memory layout (rp = r rounded up to 4, ntp = padded tap count):
+//   s_taps[ntp]            padded taps; s_taps[rp - r + j] multiplies source index x - r + j
+//   s_in  [h][iw]          column c holds source column x0 - rp + c (reflected), c < SW + ntp
+//   s_mid [h4 + ntp][SW]   row m holds the row-filtered source row m - rp (reflected above/below, zero further out)
+template <int SW, bool FMA>
+__global__ void __launch_bounds__(kStripMaxThreads) blur_strip_kernel(BlurArgs a, int iw, int ntp) {
     extern __shared__ __align__(16) float smem[];
-    const int r = a.r, w = a.w, h = a.h, nt = 2 * r + 1;
-    float* s_taps = smem;                       // s_taps[j] multiplies source index x - r + j
-    float* s_in = smem + ((nt + 3) & ~3);       // h rows x iw: source columns x0 - r .. x0 + SW + r - 1, reflected
-    float* s_mid = s_in + h * iw;               // (h + 2r) rows x SW: row-filtered lines, rows -r .. h + r - 1
+    const int r = a.r, w = a.w, h = a.h;
+    const int rp = (r + 3) & ~3, off = rp - r, h4 = (h + 3) & ~3;
+    float* s_taps = smem;
+    float* s_in = s_taps + ntp;
+    float* s_mid = s_in + h * iw;
 
     const int T = blockDim.x, tid = threadIdx.x;
     const int b = blockIdx.z + a.z0;
     const int x0 = blockIdx.x * SW;
     const float* src = a.src + (size_t)b * a.src_stride;
 
-    for (int i = tid; i < nt; i += T) s_taps[i] = a.taps[nt - 1 - i];
+    // every element is fetched with its own 4-byte cp.async (the source index is reflected per element), all of
+    // them in flight at once: the whole staging phase costs one round trip to L2 instead of one per loop trip
     {
-        // eight rows per thread in flight: the level was just written by the previous launch, so this is L2 latency
-        const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5, span = SW + 2 * r;
-        constexpr int U = 8;
+        const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5, span = SW + ntp;
         for (int tx = lane; tx < span; tx += 32) {
-            const float* colp = src + reflect101(x0 - r + tx, w);
-            for (int y = warp; y < h; y += U * nwarp) {
-                float v[U];
-#pragma unroll
-                for (int q = 0; q < U; ++q) v[q] = colp[(size_t)min(y + q * nwarp, h - 1) * a.src_pitch];
-#pragma unroll
-                for (int q = 0; q < U; ++q)
-                    if (y + q * nwarp < h) s_in[(y + q * nwarp) * iw + tx] = v[q];
-            }
+            const float* colp = src + reflect101(x0 - rp + tx, w);
+            for (int y = warp; y < h; y += nwarp) cp_async4(&s_in[y * iw + tx], colp + (size_t)y * a.src_pitch);
         }
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int i = tid; i < ntp; i += T) s_taps[i] = (i >= off && i <= off + 2 * r) ? a.taps[2 * r - (i - off)] : 0.0f;
+    // rows of s_mid the row pass does not write: reflected rows are copied after the row pass, the rest is zero
+    for (int i = tid; i < (h4 + ntp) * SW; i += T) {
+        const int m = i / SW;
+        if (m < rp || m >= rp + h) s_mid[i] = 0.0f;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
 
-    const int col = tid % SW, rg = tid / SW, rs = T / SW;  // thread = column `col`, rows rg, rg + rs, rg + 2 rs, ...
-    for (int row0 = rg; row0 < h; row0 += K * rs) {
-        const float* p[K];
-        float acc[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int y = min(row0 + k * rs, h - 1);
-            p[k] = s_in + y * iw + col;
-            acc[k] = 0.0f;
+    constexpr int CGS = SW / 4;
+    for (int id = tid; id < h * CGS; id += T) {
+        const int row = id / CGS, cg = id % CGS;
+        const float* p = s_in + row * iw + 4 * cg;
+        float4 A = *reinterpret_cast<const float4*>(p);
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+        for (int g = 0; g < ntp; g += 4) {
+            const float4 B = *reinterpret_cast<const float4*>(p + g + 4);
+            const float4 t = *reinterpret_cast<const float4*>(s_taps + g);
+            window4<FMA>(o0, o1, o2, o3, t, A.x, A.y, A.z, A.w, B.x, B.y, B.z);
+            A = B;
         }
-#pragma unroll 4
-        for (int j = 0; j < nt; ++j) {
-            const float t = s_taps[j];
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = tap_acc<FMA>(acc[k], t, p[k][j]);
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int y = row0 + k * rs;
-            if (y < h) s_mid[(y + r) * SW + col] = acc[k];
-        }
+        *reinterpret_cast<float4*>(s_mid + (row + rp) * SW + 4 * cg) = make_float4(o0, o1, o2, o3);
     }
     __syncthreads();
     for (int i = tid; i < 2 * r * SW; i += T) {
         const int q = i / SW, c = i % SW;
-        const int yy = q < r ? q - r : h + (q - r);
-        s_mid[(yy + r) * SW + c] = s_mid[(reflect101(yy, h) + r) * SW + c];
+        const int yy = q < r ? q - r : h + (q - r);  // source rows -r .. -1 and h .. h + r - 1
+        s_mid[(yy + rp) * SW + c] = s_mid[(reflect101(yy, h) + rp) * SW + c];
     }
     __syncthreads();
 
-    const int gx = x0 + col;
-    for (int row0 = rg; row0 < h; row0 += K * rs) {
-        const float* p[K];
-        float acc[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int y = min(row0 + k * rs, h - 1);
-            p[k] = s_mid + y * SW + col;  // rows y .. y + 2r of s_mid are source rows y - r .. y + r
-            acc[k] = 0.0f;
+    for (int id = tid; id < (h4 / 4) * SW; id += T) {
+        const int rg = id / SW, col = id % SW;
+        const float* p = s_mid + (4 * rg) * SW + col;  // output row y reads s_mid rows y .. y + ntp - 1
+        float a0 = p[0], a1 = p[SW], a2 = p[2 * SW], a3 = p[3 * SW];
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+        for (int g = 0; g < ntp; g += 4) {
+            const float* q = p + (g + 4) * SW;
+            const float b0 = q[0], b1 = q[SW], b2 = q[2 * SW], b3 = q[3 * SW];
+            const float4 t = *reinterpret_cast<const float4*>(s_taps + g);
+            window4<FMA>(o0, o1, o2, o3, t, a0, a1, a2, a3, b0, b1, b2);
+            a0 = b0; a1 = b1; a2 = b2; a3 = b3;
         }
-#pragma unroll 4
-        for (int j = 0; j < nt; ++j) {
-            const float t = s_taps[j];
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = tap_acc<FMA>(acc[k], t, p[k][j * SW]);
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int y = row0 + k * rs;
-            if (y < h && gx < w) store_out(a, b, gx, y, acc[k], s_in[y * iw + r + col]);
+        const int gx = x0 + col, y = 4 * rg;
+        if (gx < w) {
+            const float* centre = s_in + y * iw + rp + col;
+            store_out(a, b, gx, y, o0, centre[0]);
+            if (y + 1 < h) store_out(a, b, gx, y + 1, o1, centre[iw]);
+            if (y + 2 < h) store_out(a, b, gx, y + 2, o2, centre[2 * iw]);
+            if (y + 3 < h) store_out(a, b, gx, y + 3, o3, centre[3 * iw]);
         }
     }
 }
 
+static int strip_ntp(int r) { return (((r + 3) & ~3) - r + 2 * r + 1 + 3) & ~3; }
+
 static int strip_iw(int sw, int r) {
-    int iw = sw + 2 * r;
-    if (sw == 16) while (iw % 32 != 16) ++iw;  // two rows per warp: keep them on disjoint banks
+    int iw = sw + strip_ntp(r);                 // multiple of 4: rows stay 16-B aligned
+    if (sw == 16) while (iw % 32 != 16) iw += 4;  // two rows per quarter-warp: keep them on disjoint banks
     return iw;
 }
 
 static size_t strip_smem_bytes(int sw, int r, int h) {
-    return sizeof(float) * (size_t)(((2 * r + 1 + 3) & ~3) + h * strip_iw(sw, r) + (h + 2 * r) * sw);
+    const int h4 = (h + 3) & ~3, ntp = strip_ntp(r);
+    return sizeof(float) * (size_t)(ntp + h * strip_iw(sw, r) + (h4 + ntp) * sw);
 }
 
 static int strip_max_height() {
@@ -211,18 +226,20 @@ static int strip_max_height() {
     return v;
 }
 
-template <int SW, int K>
-static int launch_strip_k(const BlurArgs& a, int batch, bool fma, int threads, size_t smem, cudaStream_t s) {
+template <int SW>
+static int launch_strip_sw(const BlurArgs& a, int batch, bool fma, size_t smem, cudaStream_t s) {
     dim3 grid((a.w + SW - 1) / SW, 1, batch);
-    const int iw = strip_iw(SW, a.r);
+    const int iw = strip_iw(SW, a.r), ntp = strip_ntp(a.r);
+    int threads = (a.h * (SW / 4) + 31) / 32 * 32;
+    threads = threads < 64 ? 64 : (threads > kStripMaxThreads ? kStripMaxThreads : threads);
     static bool attr[2] = {false, false};
     if (!attr[fma ? 1 : 0]) {
-        if (fma) SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        else SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (fma) SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        else SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr[fma ? 1 : 0] = true;
     }
-    if (fma) blur_strip_kernel<SW, K, true><<<grid, threads, smem, s>>>(a, iw);
-    else blur_strip_kernel<SW, K, false><<<grid, threads, smem, s>>>(a, iw);
+    if (fma) blur_strip_kernel<SW, true><<<grid, threads, smem, s>>>(a, iw, ntp);
+    else blur_strip_kernel<SW, false><<<grid, threads, smem, s>>>(a, iw, ntp);
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -232,14 +249,10 @@ static int launch_strip(const BlurArgs& a, int batch, bool fma, cudaStream_t s) 
     if (a.h > strip_max_height() || a.r >= a.h || a.r >= a.w) return -1;
     const size_t cap = 200 * 1024;
     int sw = 32;
-    if (strip_smem_bytes(32, a.r, a.h) > cap || ((a.w + 31) / 32) * batch < 120) sw = 16;
+    if (strip_smem_bytes(32, a.r, a.h) > cap || ((a.w + 31) / 32) * batch < 2 * 148) sw = 16;
     const size_t smem = strip_smem_bytes(sw, a.r, a.h);
     if (smem > cap) return -1;
-    const int threads = a.h * sw >= 4096 ? 512 : 256;
-    const int per_thread = (a.h + threads / sw - 1) / (threads / sw);     // row slots of one thread
-    const bool k8 = (per_thread + 7) / 8 * 8 <= (per_thread + 3) / 4 * 4;  // K = 8 unless it wastes more slots than K = 4
-    if (sw == 32) return k8 ? launch_strip_k<32, 8>(a, batch, fma, threads, smem, s) : launch_strip_k<32, 4>(a, batch, fma, threads, smem, s);
-    return k8 ? launch_strip_k<16, 8>(a, batch, fma, threads, smem, s) : launch_strip_k<16, 4>(a, batch, fma, threads, smem, s);
+    return sw == 32 ? launch_strip_sw<32>(a, batch, fma, smem, s) : launch_strip_sw<16>(a, batch, fma, smem, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -453,6 +453,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
             }
         p->mask_words = mask_off;
         p->total_cols = (int)col_base;
+        set_scan_tiles(ps.layers_host.data(), (int)ps.layers_host.size());
         for (auto& tl : target_level)
             ps.targets_host.push_back(LevelRef{S.d_gauss[tl.first][tl.second], c->maxP[tl.first], p->pitch[tl.first], p->ow[tl.first], p->oh[tl.first]});
         if (cudaMalloc(&ps.layers_dev, sizeof(ScanLayer) * ps.layers_host.size()) != cudaSuccess ||
@@ -513,7 +514,7 @@ static int alloc_buffers(sift_gpu_ctx* c) {
             for (int i = 0; i <= D; ++i) CTX_CUDA(cudaMalloc(&S.d_gauss[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
             for (int i = 0; i < D; ++i) CTX_CUDA(cudaMalloc(&S.d_dog[o][i], sizeof(float) * c->maxP[o] * (size_t)B));
         }
-        CTX_CUDA(cudaMalloc(&S.d_mask, sizeof(uint32_t) * mask_cap * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_mask, sizeof(uint32_t) * mask_cap * (size_t)B * 2));  // candidate plane + cheap-test plane
         CTX_CUDA(cudaMalloc(&S.d_col_count, sizeof(uint32_t) * col_cap * (size_t)B));
         CTX_CUDA(cudaMalloc(&S.d_col_off, sizeof(uint32_t) * col_cap * (size_t)B));
         CTX_CUDA(cudaMalloc(&S.d_cands, sizeof(Cand) * cand_cap * (size_t)B));
@@ -603,9 +604,24 @@ static BlurArgs blur_args(const sift_gpu_ctx* c, const BlurSpec& b, const float*
 static int run_pyramid_group(sift_gpu_ctx* c, Slot& S, const Plan* p, const PlanSlot& ps, int z0, int cnt, int share, cudaStream_t s) {
     const int O = c->O, D = c->D;
     uint64_t* L = &S.launches;
+    // SIFT_GPU_TRACE_PYR: per-launch device times of the pyramid in situ (warm L2, unlike ncu's replays)
+    static const bool trace = getenv("SIFT_GPU_TRACE_PYR") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<std::string> tname;
+    auto mark = [&](const char* what, int r, int w, int h) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tev.push_back(e);
+        char buf[64];
+        snprintf(buf, sizeof buf, "%s r=%d %dx%d", what, r, w, h);
+        tname.push_back(buf);
+    };
     auto launch = [&](BlurArgs a) {
         a.z0 = z0;
         a.share = share;
+        mark(a.sel_x ? "reduce" : (a.dog ? "blur+dog" : "blur"), a.r, a.w, a.h);
         return launch_blur(a, cnt, c->fma, s, L);
     };
     const float* base_src = S.d_in;
@@ -635,6 +651,16 @@ static int run_pyramid_group(sift_gpu_ctx* c, Slot& S, const Plan* p, const Plan
             a.sel_y = p->d_maps + p->sel_y[o];
             CTX_TRY(launch(a));
         }
+    }
+    if (trace) {
+        mark("end", 0, 0, 0);
+        cudaEventSynchronize(tev.back());
+        for (size_t i = 0; i + 1 < tev.size(); ++i) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+            fprintf(stderr, "[pyr z0=%d n=%d] %-24s %8.1f us\n", z0, cnt, tname[i].c_str(), ms * 1e3f);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return 0;
 }
@@ -760,7 +786,10 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
         const size_t pitch = im.row_stride_bytes ? (size_t)im.row_stride_bytes : (size_t)im.width * esz;
         void* dst = im.dtype == SIFT_GPU_DTYPE_U8 ? (void*)(S.d_in_u8 + (size_t)b * c->max_in_px) : (void*)(S.d_in + (size_t)b * c->max_in_px);
         const cudaMemcpyKind kind = im.memory == SIFT_GPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->in_pitch * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
+        if (pitch == (size_t)im.width * esz && (size_t)p->in_pitch == (size_t)im.width)  // dense on both sides: one linear copy
+            CTX_CUDA(cudaMemcpyAsync(dst, im.data, pitch * (size_t)im.height, kind, s));
+        else
+            CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->in_pitch * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
     }
     if (S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8)
         CTX_TRY(launch_u8_to_f32(S.d_in_u8, c->max_in_px, p->in_pitch, S.d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, nb, s, L));
@@ -768,6 +797,7 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
     CTX_TRY(run_pyramid(c, S, p, ps, nb));
     CTX_CUDA(cudaEventRecord(S.ev[2], s));
     CTX_TRY(launch_extrema(ps.layers_dev, ps.layers_host.data(), (int)ps.layers_host.size(), p->total_cols, p->mask_words, S.d_mask,
+                           S.d_mask + c->mask_cap * (size_t)c->B,
                            S.d_col_count, S.d_col_off, S.d_cands, c->cand_cap, S.d_n_cand, nb, s, L));
     CTX_CUDA(cudaEventRecord(S.ev[3], s));
     CTX_TRY(launch_eliminate(ps.layers_dev, (int)ps.layers_host.size(), S.d_cands, c->cand_cap, S.d_n_cand, S.d_surv, c->cand_cap,
@@ -1345,6 +1375,7 @@ static int debug_layers_setup(sift_gpu_ctx* c, DebugLayers& S, const float* d0, 
     for (int i = 0; i < 3; ++i) CTX_TRY(upload(c, hs[i], n, &S.d[i]));
     S.L.d0 = S.d[0]; S.L.d1 = S.d[1]; S.L.d2 = S.d[2];
     S.L.stride = 0; S.L.pitch = w; S.L.w = w; S.L.h = h; S.L.n_yw = (h + 31) / 32; S.L.mask_off = 0; S.L.col_base = 0; S.L.octave = 0; S.L.index = 1;
+    set_scan_tiles(&S.L, 1);
     CTX_CUDA(cudaMalloc(&S.dev, sizeof(ScanLayer)));
     CTX_CUDA(cudaMemcpy(S.dev, &S.L, sizeof(ScanLayer), cudaMemcpyHostToDevice));
     CTX_CUDA(cudaMalloc(&S.mask, sizeof(uint32_t) * (size_t)S.L.n_yw * (size_t)w));
@@ -1361,7 +1392,7 @@ int sift_gpu_debug_extrema(sift_gpu_ctx* c, const float* d0, const float* d1, co
     CTX_CUDA(cudaSetDevice(c->prm.device));
     DebugLayers S;
     CTX_TRY(debug_layers_setup(c, S, d0, d1, d2, w, h));
-    CTX_TRY(launch_extrema(S.dev, &S.L, 1, w, (uint32_t)S.L.n_yw * (uint32_t)w, S.mask, S.cc, S.co, S.cands, 0, S.n_cand, 1, c->slots[0].stream, nullptr));
+    CTX_TRY(launch_extrema(S.dev, &S.L, 1, w, (uint32_t)S.L.n_yw * (uint32_t)w, S.mask, nullptr, S.cc, S.co, S.cands, 0, S.n_cand, 1, c->slots[0].stream, nullptr));
     CTX_CUDA(cudaStreamSynchronize(c->slots[0].stream));
     uint32_t n = 0;
     CTX_CUDA(cudaMemcpy(&n, S.n_cand, sizeof n, cudaMemcpyDeviceToHost));
