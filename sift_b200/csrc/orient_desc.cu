@@ -93,80 +93,98 @@ __device__ int find_peaks(const float* histo, float* p, float* out) {
     return n;
 }
 
-__global__ void __launch_bounds__(128) orientation_kernel(const LevelRef* __restrict__ targets, const KeyIn* __restrict__ keys,
-                                                          const uint32_t* __restrict__ key_img, uint32_t n_keys,
-                                                          float* __restrict__ orientation, uint32_t* __restrict__ n_peaks,
-                                                          float* __restrict__ peaks) {
+// Two phases per block of 32 keypoints.  Phase 1, warp per keypoint (8 keypoints per warp, one after the other): the 256
+// window samples and the 36-bin histogram.  Phase 2, THREAD per keypoint: peak logic and the least-squares parabola —
+// long scalar code that would otherwise run on one lane of a warp with the other 31 idle.
+constexpr int kOriKeys = 32;    // keypoints per CTA pass (phase 2 runs on warp 0)
+constexpr int kOriThreads = 128;
+constexpr int kHistPitch = 37;  // odd pitch: phase 2's column walk over 32 histograms is conflict-free
+
+__global__ void __launch_bounds__(kOriThreads) orientation_kernel(const LevelRef* __restrict__ targets, const KeyIn* __restrict__ keys,
+                                                               const uint32_t* __restrict__ key_img, uint32_t n_keys,
+                                                               float* __restrict__ orientation, uint32_t* __restrict__ n_peaks,
+                                                               float* __restrict__ peaks) {
     __shared__ __align__(16) float s_val[4][kWin * kWin];
     __shared__ uint16_t s_bin[4][kWin * kWin];
-    __shared__ float s_hist[4][36];
-    __shared__ float s_work[4][36], s_out[4][36];
+    __shared__ float s_hist[kOriKeys][kHistPitch];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_keys; k += warps) {
-        const KeyIn key = keys[k];
-        const LevelRef T = targets[key.tgt];
-        const float* G = T.base + (size_t)key_img[k] * T.stride;
-        const int x0 = key.x - kRegion, y0 = key.y - kRegion;
-        // sample s = wx*16 + wy is the reference's (x outer, y inner) visiting order
-        bool same_bin = true;  // do all 256 samples fall into the bin of sample 0?
-        uint16_t bin0 = 0;
+    for (uint32_t base = blockIdx.x * kOriKeys; base < n_keys; base += gridDim.x * kOriKeys) {
+        constexpr int per_warp = kOriKeys / (kOriThreads / 32);
+        for (int i = 0; i < per_warp; ++i) {
+            const int slot = wib * per_warp + i;
+            const uint32_t k = base + (uint32_t)slot;
+            if (k >= n_keys) break;  // warp-uniform
+            float* hist = s_hist[slot];
+            const KeyIn key = keys[k];
+            const LevelRef T = targets[key.tgt];
+            const float* G = T.base + (size_t)key_img[k] * T.stride;
+            const int x0 = key.x - kRegion, y0 = key.y - kRegion;
+            // sample s = wx*16 + wy is the reference's (x outer, y inner) visiting order
+            bool same_bin = true;  // do all 256 samples fall into the bin of sample 0?
+            uint16_t bin0 = 0;
 #pragma unroll
-        for (int j = 0; j < (kWin * kWin) / 32; ++j) {
-            const int s = lane + 32 * j;
-            const int wx = s >> 4, wy = s & 15;
-            float mag, ori;
-            gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &mag, &ori);
-            const float g = G[(size_t)(y0 + wy) * T.pitch + x0 + wx];
-            s_val[wib][s] = mag * g;
-            uint16_t bi = (uint16_t)(int)floorf(ori / 10);
-            bi = bi % 35;
-            s_bin[wib][s] = bi;
-            if (j == 0) bin0 = (uint16_t)__shfl_sync(0xffffffffu, (int)bi, 0);
-            same_bin = same_bin && bi == bin0;
-        }
-        same_bin = __all_sync(0xffffffffu, same_bin);
-        __syncwarp();
-        if (same_bin) {
-            // Every sample lands in one bin (with the reference's radians-as-degrees binning that is always bin 0):
-            // its sum is the plain sequential sum of the 256 products in visiting order; the other 35 bins are 0.
-            if (lane < 4) s_hist[wib][32 + lane] = 0.0f;
-            s_hist[wib][lane] = 0.0f;
+            for (int j = 0; j < (kWin * kWin) / 32; ++j) {
+                const int s = lane + 32 * j;
+                const int wx = s >> 4, wy = s & 15;
+                float mag, ori;
+                gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &mag, &ori);
+                const float g = G[(size_t)(y0 + wy) * T.pitch + x0 + wx];
+                s_val[wib][s] = mag * g;
+                uint16_t bi = (uint16_t)(int)floorf(ori / 10);
+                bi = bi % 35;
+                s_bin[wib][s] = bi;
+                if (j == 0) bin0 = (uint16_t)__shfl_sync(0xffffffffu, (int)bi, 0);
+                same_bin = same_bin && bi == bin0;
+            }
+            same_bin = __all_sync(0xffffffffu, same_bin);
             __syncwarp();
-            if (lane == 0) {
-                float acc = 0.0f;
-                const float4* v4 = reinterpret_cast<const float4*>(s_val[wib]);
+            if (same_bin) {
+                // Every sample lands in one bin (with the reference's radians-as-degrees binning that is always bin 0):
+                // its sum is the plain sequential sum of the 256 products in visiting order; the other 35 bins are 0.
+                if (lane < 4) hist[32 + lane] = 0.0f;
+                hist[lane] = 0.0f;
+                __syncwarp();
+                if (lane == 0) {
+                    float acc = 0.0f;
+                    const float4* v4 = reinterpret_cast<const float4*>(s_val[wib]);
 #pragma unroll 4
-                for (int q = 0; q < (kWin * kWin) / 4; ++q) {
-                    const float4 v = v4[q];
-                    acc = acc + v.x; acc = acc + v.y; acc = acc + v.z; acc = acc + v.w;
+                    for (int q = 0; q < (kWin * kWin) / 4; ++q) {
+                        const float4 v = v4[q];
+                        acc = acc + v.x; acc = acc + v.y; acc = acc + v.z; acc = acc + v.w;
+                    }
+                    hist[bin0] = acc;
                 }
-                s_hist[wib][bin0] = acc;
-            }
-        } else {
-            // general case: lane b owns bin b (lanes 0..3 also bins 32..35) and walks the samples in visiting order
-            float acc0 = 0.0f, acc1 = 0.0f;
-            const int binb = 32 + lane;
+            } else {
+                // general case: lane b owns bin b (lanes 0..3 also bins 32..35) and walks the samples in visiting order
+                float acc0 = 0.0f, acc1 = 0.0f;
+                const int binb = 32 + lane;
 #pragma unroll 4
-            for (int s = 0; s < kWin * kWin; ++s) {
-                const int bi = s_bin[wib][s];
-                const float v = s_val[wib][s];
-                if (bi == lane) acc0 = acc0 + v;
-                if (bi == binb) acc1 = acc1 + v;
+                for (int s = 0; s < kWin * kWin; ++s) {
+                    const int bi = s_bin[wib][s];
+                    const float v = s_val[wib][s];
+                    if (bi == lane) acc0 = acc0 + v;
+                    if (bi == binb) acc1 = acc1 + v;
+                }
+                hist[lane] = acc0;
+                if (lane < 4) hist[binb] = acc1;
             }
-            s_hist[wib][lane] = acc0;
-            if (lane < 4) s_hist[wib][binb] = acc1;
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0) {
-            float* out = s_out[wib];
-            const int n = find_peaks(s_hist[wib], s_work[wib], out);
-            orientation[k] = out[0];
-            n_peaks[k] = (uint32_t)n;
-            if (n > 1)
-                for (int i = 0; i < n; ++i) peaks[(size_t)k * 36 + i] = out[i];
+        __syncthreads();
+        {
+            const uint32_t k = base + threadIdx.x;
+            if (threadIdx.x < kOriKeys && k < n_keys) {
+                float histo[36], work[36], out[36];
+#pragma unroll
+                for (int i = 0; i < 36; ++i) histo[i] = s_hist[threadIdx.x][i];
+                const int n = find_peaks(histo, work, out);
+                orientation[k] = out[0];
+                n_peaks[k] = (uint32_t)n;
+                if (n > 1)
+                    for (int i = 0; i < n; ++i) peaks[(size_t)k * 36 + i] = out[i];
+            }
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -321,8 +339,8 @@ int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* 
                        uint64_t* launches) {
     (void)n_targets;
     if (n_keys == 0) return 0;
-    const unsigned blocks = (unsigned)((n_keys + 3) / 4);
-    orientation_kernel<<<blocks < 148u * 8u ? blocks : 148u * 8u, 128, 0, s>>>(targets_dev, keys, key_img, n_keys, orientation,
+    const unsigned blocks = (unsigned)((n_keys + kOriKeys - 1) / kOriKeys);
+    orientation_kernel<<<blocks < 148u * 8u ? blocks : 148u * 8u, kOriThreads, 0, s>>>(targets_dev, keys, key_img, n_keys, orientation,
                                                                                 n_peaks, peaks);
     if (launches) ++*launches;
     SIFT_CUDA_TRY(cudaGetLastError());

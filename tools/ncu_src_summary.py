@@ -9,7 +9,7 @@ def main(path, top=25):
     hdr = rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    body = rows[2:]
+    body = [r for r in rows[2:] if len(r) > 2 and r[2].strip().isdigit()]
     tot = sum(int(r[2]) for r in body)
     print(rows[0][1][:120])
     print("total samples", tot, " instructions executed (warp):", sum(int(r[col['Instructions Executed']]) for r in body))
