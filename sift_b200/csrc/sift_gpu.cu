@@ -780,16 +780,27 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
     S.launches = 0;
     CTX_CUDA(cudaEventRecord(S.ev[0], s));
     // upload (main.cpp:52-54 leaves band 0 as float 0..255; u8 input is widened on the device)
-    for (int b = 0; b < nb; ++b) {
+    for (int b = 0; b < nb;) {
         const sift_gpu_image& im = *S.imgs[(size_t)b].img;
         const size_t esz = im.dtype == SIFT_GPU_DTYPE_U8 ? 1 : 4;
         const size_t pitch = im.row_stride_bytes ? (size_t)im.row_stride_bytes : (size_t)im.width * esz;
         void* dst = im.dtype == SIFT_GPU_DTYPE_U8 ? (void*)(S.d_in_u8 + (size_t)b * c->max_in_px) : (void*)(S.d_in + (size_t)b * c->max_in_px);
         const cudaMemcpyKind kind = im.memory == SIFT_GPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        if (pitch == (size_t)im.width * esz && (size_t)p->in_pitch == (size_t)im.width)  // dense on both sides: one linear copy
-            CTX_CUDA(cudaMemcpyAsync(dst, im.data, pitch * (size_t)im.height, kind, s));
-        else
+        const size_t bytes = pitch * (size_t)im.height;
+        if (pitch == (size_t)im.width * esz && (size_t)p->in_pitch == (size_t)im.width) {
+            // dense on both sides: one linear copy, extended over the following frames while they are adjacent in the
+            // caller's memory and in the staging buffer (a frame stack uploads as a single transfer)
+            int n = 1;
+            if ((size_t)p->in_pitch * (size_t)p->in_h == c->max_in_px)
+                while (b + n < nb && S.imgs[(size_t)(b + n)].img->memory == im.memory && (!S.imgs[(size_t)(b + n)].img->row_stride_bytes || (size_t)S.imgs[(size_t)(b + n)].img->row_stride_bytes == pitch) &&
+                       (const char*)S.imgs[(size_t)(b + n)].img->data == (const char*)im.data + (size_t)n * bytes)
+                    ++n;
+            CTX_CUDA(cudaMemcpyAsync(dst, im.data, bytes * (size_t)n, kind, s));
+            b += n;
+        } else {
             CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->in_pitch * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
+            ++b;
+        }
     }
     if (S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8)
         CTX_TRY(launch_u8_to_f32(S.d_in_u8, c->max_in_px, p->in_pitch, S.d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, nb, s, L));
