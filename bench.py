@@ -52,7 +52,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_begin = [], None, index, None
 
     def start(self):
         try:
@@ -64,13 +64,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        """Start of the timed region: nvidia-smi is started before the warm-up (its first sample takes ~1 s), samples
+        taken during the warm-up are only used if the timed region turns out shorter than one sampling period."""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        t_end = time.perf_counter()
+        inside = [r for t, r in self.rows if self.t_begin is None or self.t_begin <= t <= t_end + 0.15]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for _, r in self.rows[-5:]], "warm-up just before the timed region (region shorter than one sample)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -80,7 +90,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def run_reference(args):
@@ -145,6 +155,26 @@ def cpu_baseline_sample(seconds_budget=12.0):
             "sample": f"{n} synthetic 1080p frames, oracle 'hoisted' flavour (reference results without its O(pixels^2) copies), 1 thread"}
 
 
+def bind_to_gpu_cpus(index):
+    """Multi-GPU host: keep this rank's threads and its pinned buffers on the CPUs (NUMA node) next to its GPU, so the frame
+    uploads do not cross the socket interconnect.  Best effort; returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        mine = near & os.sched_getaffinity(0)
+        if mine:
+            os.sched_setaffinity(0, mine)
+            return len(mine)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -156,6 +186,7 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     dist = shard.init_process_group("nccl") if world > 1 else None
 
@@ -197,14 +228,16 @@ def run_ours(args):
         return acc
 
     def timed(base_ptr, memory, dtype=capi.DTYPE_F32):
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
         do_steps(base_ptr, memory, args.warmup, 0, dtype)
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
-        if sampler:
-            sampler.start()
         torch.cuda.synchronize()
+        if sampler:
+            sampler.mark_begin()
         t0 = time.perf_counter()
         acc = do_steps(base_ptr, memory, args.steps, args.warmup, dtype)
         torch.cuda.synchronize()
@@ -269,7 +302,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (distinct frames cycled: %d MB per GPU)" % (n_distinct * per_img_h2d // 1000000),
                    "order": "canonical" if args.flags & capi.FLAG_ORDER_CANONICAL else "reference std::sort replay",
                    "blur": "fma" if args.flags & capi.FLAG_FMA_BLUR else "exact mul+add (bit-identical to the oracle)",
-                   "keypoints_per_image": kps / images, "candidates_per_image": cands / images},
+                   "keypoints_per_image": kps / images, "candidates_per_image": cands / images,
+                   "host_cpus": len(os.sched_getaffinity(0)), "bound_to_gpu_numa_cpus": numa},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * per_img_h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * wall_h / args.steps},
@@ -283,6 +317,7 @@ def run_ours(args):
                      "measured": "serial context (SIFT_GPU_FLAG_SERIAL), %d steps, CUDA events around the stage" % n_roof, "traffic": traffic,
                      "serial_stage_ms_per_image": {k2: v / (n_roof * B) for k2, v in acc_r["stages"].items()}},
         "device_span_ms_per_step": span_d / args.steps,
+        "timing": "host clock around K synchronous library calls, bracketed by cuda synchronize + barrier, max over ranks; device_span_ms_per_step is the CUDA-event span (first to last stream event of each call) of the same steps",
         "stage_ms_per_image": {k2: v / (args.steps * B) for k2, v in acc_d["stages"].items()},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -722,8 +722,25 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
                          ReplayOut* out) {
     const bool canonical = (c->prm.flags & SIFT_GPU_FLAG_ORDER_CANONICAL) != 0;
     const int D = c->D;
+    // the device appends survivors in arbitrary order: back to canonical order with an LSD radix sort on `canon` (< n_cand)
     std::vector<Surv> S(surv_in, surv_in + n_surv);
-    std::sort(S.begin(), S.end(), [](const Surv& a, const Surv& b) { return a.canon < b.canon; });
+    {
+        std::vector<Surv> tmp(n_surv);
+        int bits = 1;
+        while (bits < 32 && (n_cand >> bits) != 0) ++bits;
+        const int passes = (bits + 10) / 11;
+        Surv* src = S.data();
+        Surv* dst = tmp.data();
+        for (int ps = 0; ps < passes; ++ps) {
+            uint32_t count[2049] = {0};
+            const int sh = 11 * ps;
+            for (uint32_t i = 0; i < n_surv; ++i) ++count[((src[i].canon >> sh) & 2047u) + 1];
+            for (int i = 0; i < 2048; ++i) count[i + 1] += count[i];
+            for (uint32_t i = 0; i < n_surv; ++i) dst[count[(src[i].canon >> sh) & 2047u]++] = src[i];
+            std::swap(src, dst);
+        }
+        if (src != S.data()) S.swap(tmp);
+    }
     // first cleanup over all candidates
     std::vector<uint32_t> L1;  // survivor slots in vector order
     {
@@ -1131,7 +1148,8 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
     }
     int nthreads = 0;
     if (const char* e = getenv("SIFT_GPU_HOST_THREADS")) nthreads = atoi(e);
-    if (nthreads <= 0) nthreads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    // default: the host's hardware threads shared out over its GPUs (one process per GPU is the deployment), at most 16
+    if (nthreads <= 0) nthreads = (int)std::min<unsigned>(16u, std::max(4u, std::thread::hardware_concurrency() / (unsigned)std::max(1, ndev)));
     c->pool = new Pool(nthreads - 1);
     *out = c;
     return SIFT_GPU_OK;
