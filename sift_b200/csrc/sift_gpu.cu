@@ -83,24 +83,35 @@ class Pool {
         cv.notify_all();
         for (auto& t : workers) t.join();
     }
-    void parallel_for(int n, const std::function<void(int)>& fn) {
-        if (n <= 0) return;
-        if (workers.empty() || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    // begin() hands fn(0..n-1) to the workers and returns; end() lets the caller take what is left and waits for the rest.
+    void begin(int n, std::function<void(int)> fn) {
+        held = std::move(fn);
+        held_n = n;
+        if (n <= 0 || workers.empty()) return;
         {
             std::lock_guard<std::mutex> g(m);
-            job = &fn; next = 0; total = n; pending = n;
+            job = &held; next = 0; total = n; pending = n;
         }
         cv.notify_all();
-        // the caller helps
+    }
+    void end() {
+        const int n = held_n;
+        held_n = 0;
+        if (n <= 0) return;
+        if (workers.empty()) { for (int i = 0; i < n; ++i) held(i); return; }
         for (;;) {
             int i = next.fetch_add(1);
             if (i >= n) break;
-            fn(i);
+            held(i);
             if (pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m); done_cv.notify_all(); }
         }
         std::unique_lock<std::mutex> lk(m);
         done_cv.wait(lk, [this] { return pending.load() == 0; });
         job = nullptr;
+    }
+    void parallel_for(int n, const std::function<void(int)>& fn) {
+        begin(n, fn);
+        end();
     }
 
    private:
@@ -125,6 +136,8 @@ class Pool {
     std::mutex m;
     std::condition_variable cv, done_cv;
     const std::function<void(int)>* job = nullptr;
+    std::function<void(int)> held;
+    int held_n = 0;
     std::atomic<int> next{0}, pending{0};
     int total = 0;
     bool stop = false;
@@ -231,6 +244,7 @@ struct Slot {
     std::vector<ReplayOut> rep;
     size_t n_keys = 0;
     float* h_desc = nullptr;
+    double t_replay0 = 0.0;
     uint64_t launches = 0;
     bool busy = false;
 };
@@ -503,7 +517,9 @@ static int alloc_buffers(sift_gpu_ctx* c) {
         for (auto& st : S.aux) CTX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CTX_CUDA(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
         for (auto& e : S.ev_join) CTX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto& e : S.ev) CTX_CUDA(cudaEventCreate(&e));
+        // the host waits on these: block instead of spinning, a spinning waiter per GPU starves the replay workers of the
+        // other ranks on a host with few cores per GPU
+        for (auto& e : S.ev) CTX_CUDA(cudaEventCreateWithFlags(&e, cudaEventBlockingSync));
         CTX_CUDA(cudaMalloc(&S.d_in_u8, c->max_in_px * (size_t)B));
         CTX_CUDA(cudaMalloc(&S.d_in, sizeof(float) * c->max_in_px * (size_t)B));
         if (c->prm.subpixel) {
@@ -529,7 +545,7 @@ static int alloc_buffers(sift_gpu_ctx* c) {
         S.surv_overflow.resize((size_t)B);
     }
     CTX_CUDA(cudaEventCreate(&c->ev_first));
-    CTX_CUDA(cudaEventCreate(&c->ev_last));
+    CTX_CUDA(cudaEventCreateWithFlags(&c->ev_last, cudaEventBlockingSync));
     return 0;
 }
 
@@ -701,6 +717,8 @@ static void cleanup_order(uint32_t n, const std::vector<uint32_t>& zero_pos, boo
     kept->resize((uint16_t)zero_pos.size());  // u16_t size = distance(begin, first filtered) (sift.cpp:41)
 }
 
+static std::atomic<long> g_rep_ns[6];  // SIFT_GPU_TRACE: CPU time inside replay_image by phase (summed over worker threads)
+
 // Fills the result record of a point that reached _createDecriptors; returns whether it gets a descriptor.
 static bool make_keypoint(const sift_gpu_ctx* c, const Plan* p, const Surv& s, sift_gpu_keypoint* k, KeyIn* ki) {
     const int slot = p->class_target[(size_t)(s.octave * c->D + s.index)];
@@ -722,6 +740,13 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
                          ReplayOut* out) {
     const bool canonical = (c->prm.flags & SIFT_GPU_FLAG_ORDER_CANONICAL) != 0;
     const int D = c->D;
+    auto tick = [] { return std::chrono::steady_clock::now(); };
+    auto lap = [](int i, std::chrono::steady_clock::time_point& t) {
+        const auto n = std::chrono::steady_clock::now();
+        g_rep_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count();
+        t = n;
+    };
+    auto t_ph = tick();
     // the device appends survivors in arbitrary order: back to canonical order with an LSD radix sort on `canon` (< n_cand)
     std::vector<Surv> S(surv_in, surv_in + n_surv);
     {
@@ -741,6 +766,7 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
         }
         if (src != S.data()) S.swap(tmp);
     }
+    lap(0, t_ph);
     // first cleanup over all candidates
     std::vector<uint32_t> L1;  // survivor slots in vector order
     {
@@ -749,6 +775,7 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
         cleanup_order(n_cand, zero_pos, canonical, &L1);
     }
     out->n_survivors = (uint32_t)L1.size();
+    lap(1, t_ph);
     // _orientationAssignment bounds test (sift.cpp:173-178) and the dead blur's precondition (sift.cpp:184)
     std::vector<uint32_t> inside;  // positions in L1 that pass the bounds test
     for (size_t i = 0; i < L1.size(); ++i) {
@@ -762,8 +789,10 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
             return;
         }
     }
+    lap(2, t_ph);
     std::vector<uint32_t> L2;  // indices into `inside`
     cleanup_order((uint32_t)L1.size(), inside, canonical, &L2);
+    lap(3, t_ph);
     out->truncated = L2.size() != inside.size();
     out->l1.resize(L1.size());
     for (size_t i = 0; i < L1.size(); ++i) out->l1[i] = S[L1[i]];
@@ -780,6 +809,7 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
         }
     }
     out->inside.swap(inside);
+    lap(4, t_ph);
 }
 
 static double g_trace[8];  // SIFT_GPU_TRACE: host wall time per phase of the pass loop (diagnostics only)
@@ -846,17 +876,17 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
     return 0;
 }
 
-// Host order replay of one pass (blocks on stage A), then stage B: keypoints up, orientation, descriptors, results back.
-static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) {
+// Host order replay of one pass, first half: blocks on stage A, then starts the per-image replay on the worker pool and
+// returns (the caller collects an older pass and enqueues the next stage A meanwhile).
+static int begin_replay(sift_gpu_ctx* c, Slot& S) {
     Plan* p = S.plan;
-    const PlanSlot& ps = p->ps[slot_index];
     const int nb = (int)S.imgs.size();
     cudaStream_t s = S.stream;
-    uint64_t* L = &S.launches;
     const double t_w0 = now_ms();
     CTX_CUDA(cudaEventSynchronize(S.ev[5]));
     g_trace[1] += now_ms() - t_w0;
     // images with more survivors than the speculative copy holds fetch the remainder now (rare)
+    bool overflow = false;
     for (int b = 0; b < nb; ++b) {
         S.surv_overflow[(size_t)b].clear();
         const uint32_t n = S.h_n_surv[b];
@@ -864,17 +894,31 @@ static int replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) 
         if (n > kSurvFirst) {
             S.surv_overflow[(size_t)b].resize(n);
             CTX_CUDA(cudaMemcpyAsync(S.surv_overflow[(size_t)b].data(), S.d_surv + (size_t)b * c->cand_cap, sizeof(Surv) * n, cudaMemcpyDeviceToHost, s));
+            overflow = true;
         }
     }
-    CTX_CUDA(cudaStreamSynchronize(s));
+    if (overflow) CTX_CUDA(cudaStreamSynchronize(s));
 
-    const double t_host0 = now_ms();
+    S.t_replay0 = now_ms();
     S.rep.assign((size_t)nb, ReplayOut());
-    c->pool->parallel_for(nb, [&](int b) {
-        const uint32_t n = S.h_n_surv[b];
-        const Surv* sv = n > kSurvFirst ? S.surv_overflow[(size_t)b].data() : S.h_surv + (size_t)b * kSurvFirst;
-        replay_image(c, p, S.h_n_cand[b], sv, n, &S.rep[(size_t)b]);
+    Slot* Sp = &S;
+    c->pool->begin(nb, [c, p, Sp](int b) {
+        const uint32_t n = Sp->h_n_surv[b];
+        const Surv* sv = n > kSurvFirst ? Sp->surv_overflow[(size_t)b].data() : Sp->h_surv + (size_t)b * kSurvFirst;
+        replay_image(c, p, Sp->h_n_cand[b], sv, n, &Sp->rep[(size_t)b]);
     });
+    return 0;
+}
+
+// Second half: waits for the replay, then stage B: keypoints up, orientation, descriptors, results back.
+static int end_replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_index) {
+    Plan* p = S.plan;
+    const PlanSlot& ps = p->ps[slot_index];
+    const int nb = (int)S.imgs.size();
+    cudaStream_t s = S.stream;
+    uint64_t* L = &S.launches;
+    c->pool->end();
+    const double t_host0 = S.t_replay0;
     size_t n_keys = 0;
     for (int b = 0; b < nb; ++b) {
         S.h_key_first[b] = (uint32_t)n_keys;
@@ -1248,30 +1292,49 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
     int lag_b = ns >= 4 ? ns - 2 : (ns >= 2 ? 1 : 0);
     if (const char* e = getenv("SIFT_GPU_LAG")) lag_b = std::max(ns >= 2 ? 1 : 0, std::min(ns - 1, atoi(e)));
     const int lag_f = ns - 1;
-    for (int k = 0; k < np + lag_f; ++k) {
-        if (k < np) {
-            Slot& S = c->slots[k % ns];
-            S.plan = passes[(size_t)k].plan;
-            S.imgs = passes[(size_t)k].imgs;
-            S.busy = true;
-            if (k == 0) CTX_CUDA(cudaEventRecord(c->ev_first, S.stream));
-            const double t_a0 = now_ms();
-            CTX_TRY(enqueue_stage_a(c, S, k % ns));
-            g_trace[0] += now_ms() - t_a0;
+    auto collect = [&](int kf) -> int {
+        Slot& S = c->slots[kf % ns];
+        if (kf == np - 1) CTX_CUDA(cudaEventRecord(c->ev_last, S.stream));
+        CTX_TRY(finish_pass(c, S, kf % ns, results));
+        c->last_slot = kf % ns;
+        for (const ChunkImage& ci : S.imgs)
+            if (results[ci.result_index].status != SIFT_GPU_OK && !first_error) {
+                first_error = results[ci.result_index].status;
+                if (first_error == SIFT_GPU_E_PRECONDITION) c->error = "separableConvolveX(): kernel longer than line";
+            }
+        return 0;
+    };
+    auto stage_a = [&](int k) -> int {
+        Slot& S = c->slots[k % ns];
+        S.plan = passes[(size_t)k].plan;
+        S.imgs = passes[(size_t)k].imgs;
+        S.busy = true;
+        if (k == 0) CTX_CUDA(cudaEventRecord(c->ev_first, S.stream));
+        const double t_a0 = now_ms();
+        CTX_TRY(enqueue_stage_a(c, S, k % ns));
+        g_trace[0] += now_ms() - t_a0;
+        return 0;
+    };
+    if (lag_b >= 1 && ns >= 3) {
+        // Iteration k: the replay of pass k - lag_b runs on the worker pool while this thread collects pass k - ns (which
+        // frees the slot) and enqueues stage A of pass k; then it joins the replay and enqueues that pass's stage B.
+        for (int k = 0; k < np + ns; ++k) {
+            const int kb = k - lag_b;
+            const bool rb = kb >= 0 && kb < np;
+            if (rb) CTX_TRY(begin_replay(c, c->slots[kb % ns]));
+            if (k - ns >= 0 && k - ns < np) CTX_TRY(collect(k - ns));
+            if (k < np) CTX_TRY(stage_a(k));
+            if (rb) CTX_TRY(end_replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
         }
-        const int kb = k - lag_b;
-        if (kb >= 0 && kb < np) CTX_TRY(replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
-        const int kf = k - lag_f;
-        if (kf >= 0 && kf < np) {
-            Slot& S = c->slots[kf % ns];
-            if (kf == np - 1) CTX_CUDA(cudaEventRecord(c->ev_last, S.stream));
-            CTX_TRY(finish_pass(c, S, kf % ns, results));
-            c->last_slot = kf % ns;
-            for (const ChunkImage& ci : S.imgs)
-                if (results[ci.result_index].status != SIFT_GPU_OK && !first_error) {
-                    first_error = results[ci.result_index].status;
-                    if (first_error == SIFT_GPU_E_PRECONDITION) c->error = "separableConvolveX(): kernel longer than line";
-                }
+    } else {
+        for (int k = 0; k < np + lag_f; ++k) {
+            if (k < np) CTX_TRY(stage_a(k));
+            const int kb = k - lag_b;
+            if (kb >= 0 && kb < np) {
+                CTX_TRY(begin_replay(c, c->slots[kb % ns]));
+                CTX_TRY(end_replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
+            }
+            if (k - lag_f >= 0 && k - lag_f < np) CTX_TRY(collect(k - lag_f));
         }
     }
     if (np > 0) {
@@ -1287,6 +1350,11 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
         fprintf(stderr, "[sift_gpu trace] %d passes, wall %.2f ms: enqueueA %.2f  waitA %.2f  replay %.2f  enqueueB %.2f  waitC %.2f  collect %.2f\n", np,
                 c->tm.wall_ms, g_trace[0], g_trace[1], g_trace[2], g_trace[3], g_trace[4], g_trace[5]);
     }
+    if (getenv("SIFT_GPU_TRACE"))
+        fprintf(stderr, "[sift_gpu replay cpu] per image: radix %.1f us  sort1 %.1f  bounds %.1f  sort2 %.1f  keypoints %.1f\n", g_rep_ns[0] * 1e-3 / std::max(1, n_images),
+                g_rep_ns[1] * 1e-3 / std::max(1, n_images), g_rep_ns[2] * 1e-3 / std::max(1, n_images), g_rep_ns[3] * 1e-3 / std::max(1, n_images),
+                g_rep_ns[4] * 1e-3 / std::max(1, n_images));
+    for (auto& v : g_rep_ns) v = 0;
     for (double& v : g_trace) v = 0.0;
     return first_error;
 }
