@@ -16,6 +16,7 @@
 #include <functional>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <string>
 #include <thread>
 #include <vector>
@@ -246,6 +247,9 @@ struct Slot {
     float* h_desc = nullptr;
     double t_replay0 = 0.0;
     uint64_t launches = 0;
+    // stage A between upload and the survivor copy-back as an instantiated CUDA graph per (plan, images in the pass, input dtype)
+    struct StageGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int seen = 0; };
+    std::map<std::tuple<const void*, int, int>, StageGraph> graphs;
     bool busy = false;
 };
 
@@ -800,6 +804,7 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
     out->key_of.assign(L2.size(), ~0u);
     out->kp_l1.resize(L2.size());
     out->keys.clear();
+    out->keys.reserve(L2.size());
     for (size_t i = 0; i < L2.size(); ++i) {
         out->kp_l1[i] = inside[L2[i]];
         KeyIn ki;
@@ -849,24 +854,57 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
             ++b;
         }
     }
-    if (S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8)
-        CTX_TRY(launch_u8_to_f32(S.d_in_u8, c->max_in_px, p->in_pitch, S.d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, nb, s, L));
-    CTX_CUDA(cudaEventRecord(S.ev[1], s));
-    CTX_TRY(run_pyramid(c, S, p, ps, nb));
-    CTX_CUDA(cudaEventRecord(S.ev[2], s));
-    CTX_TRY(launch_extrema(ps.layers_dev, ps.layers_host.data(), (int)ps.layers_host.size(), p->total_cols, p->mask_words, S.d_mask,
-                           S.d_mask + c->mask_cap * (size_t)c->B,
-                           S.d_col_count, S.d_col_off, S.d_cands, c->cand_cap, S.d_n_cand, nb, s, L));
-    CTX_CUDA(cudaEventRecord(S.ev[3], s));
-    CTX_TRY(launch_eliminate(ps.layers_dev, (int)ps.layers_host.size(), S.d_cands, c->cand_cap, S.d_n_cand, S.d_surv, c->cand_cap,
-                             S.d_n_surv, c->D, nb, s, L));
-    CTX_CUDA(cudaEventRecord(S.ev[4], s));
-    CTX_CUDA(cudaMemcpyAsync(S.h_n_cand, S.d_n_cand, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(cudaMemcpyAsync(S.h_n_surv, S.d_n_surv, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
-    // speculative: the first kSurvFirst survivors of every image travel with the counters (one strided copy)
-    const size_t first = std::min<size_t>(kSurvFirst, c->cand_cap);
-    CTX_CUDA(cudaMemcpy2DAsync(S.h_surv, sizeof(Surv) * kSurvFirst, S.d_surv, sizeof(Surv) * c->cand_cap, sizeof(Surv) * first, (size_t)nb,
-                               cudaMemcpyDeviceToHost, s));
+    // Everything from here to the survivor copy-back has the same launches, the same device addresses and the same kernel
+    // parameters every time this slot sees a pass of this shape: the second time it is captured into a CUDA graph (both
+    // pyramid streams, the stage-boundary events as external event-record nodes) and from then on one graph launch
+    // replaces ~50 launch calls — less host time per pass and shorter gaps between the short kernels of the small octaves.
+    static const bool graphs_on = [] { const char* e = getenv("SIFT_GPU_GRAPHS"); return !(e && atoi(e) == 0) && !getenv("SIFT_GPU_TRACE_PYR"); }();
+    const bool u8 = S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8;
+    Slot::StageGraph* G = graphs_on ? &S.graphs[std::make_tuple((const void*)p, nb, u8 ? 1 : 0)] : nullptr;
+    if (G && G->exec) {
+        CTX_CUDA(cudaGraphLaunch(G->exec, s));
+        S.launches += G->launches;
+    } else {
+        const bool capture = G && G->seen >= 1;  // the first pass of a shape runs eagerly (attribute set-up, occupancy queries)
+        if (G) ++G->seen;
+        const uint64_t l0 = S.launches;
+        if (capture) CTX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        auto mark = [&](int i) { return capture ? cudaEventRecordWithFlags(S.ev[i], s, cudaEventRecordExternal) : cudaEventRecord(S.ev[i], s); };
+        int rc = 0;
+        auto body = [&]() -> int {
+            if (u8) CTX_TRY(launch_u8_to_f32(S.d_in_u8, c->max_in_px, p->in_pitch, S.d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, nb, s, L));
+            CTX_CUDA(mark(1));
+            CTX_TRY(run_pyramid(c, S, p, ps, nb));
+            CTX_CUDA(mark(2));
+            CTX_TRY(launch_extrema(ps.layers_dev, ps.layers_host.data(), (int)ps.layers_host.size(), p->total_cols, p->mask_words, S.d_mask,
+                                   S.d_mask + c->mask_cap * (size_t)c->B, S.d_col_count, S.d_col_off, S.d_cands, c->cand_cap, S.d_n_cand, nb, s, L));
+            CTX_CUDA(mark(3));
+            CTX_TRY(launch_eliminate(ps.layers_dev, (int)ps.layers_host.size(), S.d_cands, c->cand_cap, S.d_n_cand, S.d_surv, c->cand_cap,
+                                     S.d_n_surv, c->D, nb, s, L));
+            CTX_CUDA(mark(4));
+            CTX_CUDA(cudaMemcpyAsync(S.h_n_cand, S.d_n_cand, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+            CTX_CUDA(cudaMemcpyAsync(S.h_n_surv, S.d_n_surv, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+            // speculative: the first kSurvFirst survivors of every image travel with the counters (one strided copy)
+            const size_t first = std::min<size_t>(kSurvFirst, c->cand_cap);
+            CTX_CUDA(cudaMemcpy2DAsync(S.h_surv, sizeof(Surv) * kSurvFirst, S.d_surv, sizeof(Surv) * c->cand_cap, sizeof(Surv) * first, (size_t)nb,
+                                       cudaMemcpyDeviceToHost, s));
+            return 0;
+        };
+        rc = body();
+        if (capture) {
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            CTX_CUDA(e);
+            const cudaError_t ei = cudaGraphInstantiate(&G->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            CTX_CUDA(ei);
+            G->launches = S.launches - l0;
+            CTX_CUDA(cudaGraphLaunch(G->exec, s));
+        } else if (rc) {
+            return rc;
+        }
+    }
     if (c->prm.subpixel && (c->prm.flags & SIFT_GPU_FLAG_KEEP_UPSAMPLED))
         for (int b = 0; b < nb; ++b)
             if (S.imgs[(size_t)b].img->upsampled_out)
@@ -1216,6 +1254,8 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
         cudaFree(S.d_in_u8); cudaFree(S.d_in); cudaFree(S.d_up_tmp); cudaFree(S.d_up);
         for (int o = 0; o < kMaxOctaves; ++o)
             for (int i = 0; i < kMaxGauss; ++i) { cudaFree(S.d_gauss[o][i]); cudaFree(S.d_dog[o][i]); }
+        for (auto& kv : S.graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        S.graphs.clear();
         cudaFree(S.d_mask); cudaFree(S.d_col_count); cudaFree(S.d_col_off); cudaFree(S.d_cands); cudaFree(S.d_surv);
         cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv);
         cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_key_first); cudaFree(S.d_orient); cudaFree(S.d_npeaks);
