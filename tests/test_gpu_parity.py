@@ -83,6 +83,24 @@ def test_extra_orientation_peaks_mixed_batch(built):
     g.close()
 
 
+def test_repeated_runs_replay_the_captured_stage_graph(built):
+    """The first pass of a shape on a slot runs eagerly, the second is captured into a CUDA graph, later ones replay it:
+    every run must give the oracle's result, with different frames flowing through the same graph."""
+    frames = [synth_frame(320, 240, s) for s in range(4)]
+    ref = [ol.Oracle(3, 3, 1.6, K, False).calculate(f) for f in frames]
+    g = capi.SiftGpu(3, 3, 1.6, K, False, max_width=320, max_height=240, max_batch=2)
+    for rnd in range(4):
+        order = [(rnd + i) % 4 for i in range(4)]
+        res = g.run([frames[i] for i in order])
+        for i, r in zip(order, res):
+            okp = ref[i]
+            assert r["status"] == 0 and r["kps"].size == okp["x"].size, (rnd, i)
+            for f in ("x", "y", "octave", "index", "orientation", "filtered"):
+                assert np.array_equal(r["kps"][f], okp[f]), (rnd, i, f)
+            assert np.array_equal(r["desc"], okp["desc"]), (rnd, i)
+    g.close()
+
+
 def test_config1_parrot_defaults(built, parrot):
     """BASELINE config 1: example/parrot.jpg band 0, sigma 1.6, k sqrt2, 4 octaves, 3 DoGs, subpixel 0."""
     kp = full_compare(parrot, 4)
