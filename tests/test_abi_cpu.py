@@ -143,3 +143,40 @@ def test_bench_pyramid_bytes_match_survey():
     assert abs(bench.pyramid_bytes(488, 600, 4, 3, False) / 1e6 - 16.71) < 0.01      # config 1
     assert abs(bench.pyramid_bytes(600, 600, 4, 3, True) / 1e6 - 80.73) < 0.01       # config 2
     assert abs(bench.pyramid_bytes(3840, 2160, 6, 3, True) / 1e6 - 1868.44) < 0.05   # config 4
+
+
+def test_keypoint_overlay_matches_the_reference_geometry(built):
+    """main.cpp:59-75: rotated square of side int(scale*10) at (x*2^octave/div, y*2^octave/div), blue outline."""
+    import ctypes
+
+    lib = ctypes.CDLL(os.path.join(ROOT, "sift_b200", "libsift_host.so"))
+    lib.sift_host_draw_points.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.sift_host_draw_points.restype = None
+
+    def draw(pts, w=200, h=160, subpixel=0, fill=7):
+        img = np.full((h, w, 3), fill, np.uint8)
+        p = np.asarray(pts, np.float32).reshape(-1, 5)
+        lib.sift_host_draw_points(img.ctypes.data, w, h, p.ctypes.data, p.shape[0], subpixel)
+        return img
+
+    blue = np.array([0, 0, 255], np.uint8)
+    # orientation 0: axis-aligned square of side int(1.6*10) = 16 centred at (50, 40) * 2^1 = (100, 80)
+    img = draw([[50, 40, 1, 1.6, 0.0]])
+    on = np.all(img == blue, axis=2)
+    ys, xs = np.nonzero(on)
+    assert xs.min() == 92 and xs.max() == 108 and ys.min() == 72 and ys.max() == 88
+    assert on[72, 92:109].all() and on[88, 92:109].all() and on[72:89, 92].all() and on[72:89, 108].all()
+    assert on.sum() == 4 * 16 and not on[80, 100]          # outline only
+    assert np.all(img[~on] == 7)                            # nothing else touched
+    # 90 degrees gives the same square; 45 degrees a diamond whose corners sit on the axes
+    assert np.array_equal(np.all(draw([[50, 40, 1, 1.6, 90.0]]) == blue, axis=2), on)
+    d = np.all(draw([[50, 40, 1, 1.6, 45.0]]) == blue, axis=2)
+    ys, xs = np.nonzero(d)
+    assert abs((xs.max() - xs.min()) - 16 * np.sqrt(2)) <= 1.5 and d[80, xs.min()] and d[ys.min(), 100]
+    # subpixel halves the coordinates (main.cpp:60); scale is not rescaled
+    s = np.all(draw([[50, 40, 1, 1.6, 0.0]], subpixel=1) == blue, axis=2)
+    ys, xs = np.nonzero(s)
+    assert (xs.min(), xs.max(), ys.min(), ys.max()) == (42, 58, 32, 48)
+    # clipping: a square hanging over the border, a huge one, NaN orientation (flat window) — no crash, pixels stay inside
+    img = draw([[2, 2, 0, 3.0, 30.0], [100, 80, 0, 500.0, 12.0], [60, 60, 0, 2.0, float("nan")]])
+    assert img.shape == (160, 200, 3)

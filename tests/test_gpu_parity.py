@@ -362,3 +362,8 @@ def test_cli_text_output_equals_oracle_text(built, parrot, tmp_path):
     o = ol.Oracle(3, 4, 1.6, K, False)
     o.calculate(parrot)
     assert open(out).read() == o.text()
+    # main.cpp:59-76: the overlay image is written next to the input
+    ov = open(str(pgm) + "_orientation.ppm", "rb").read()
+    assert ov.startswith(b"P6\n488 600\n255\n")
+    px = np.frombuffer(ov[len(b"P6\n488 600\n255\n"):], np.uint8).reshape(600, 488, 3)
+    assert int(np.all(px == np.array([0, 0, 255], np.uint8), axis=2).sum()) > 1507  # every keypoint left an outline
