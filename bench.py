@@ -254,6 +254,17 @@ def run_ours(args):
     host_u8 = host_frames.to(torch.uint8).pin_memory()
     wall_u8, acc_u8, _ = timed(host_u8.data_ptr(), capi.MEM_HOST, capi.DTYPE_U8)
 
+    # single-image latency, one 1080p frame from pinned host memory to keypoints + descriptors in host
+    # memory (no batching, nothing to overlap with)
+    lat = []
+    one = (capi.Image * 1)()
+    for i in range(12):
+        one[0] = capi.Image(host_frames.data_ptr() + (i % n_distinct) * W * H * 4, W, H, 0, capi.DTYPE_F32, capi.MEM_HOST, None)
+        t0 = time.perf_counter()
+        g.run_raw(one, 1)
+        lat.append(1e3 * (time.perf_counter() - t0))
+    latency_ms = sorted(lat[2:])[len(lat[2:]) // 2]
+
     # Roofline of the pyramid + DoG stage: in the pipelined runs above three device passes overlap, so a stage's
     # CUDA-event duration includes other passes' kernels.  Time the stage on a serial context (one pass at a time,
     # same kernels, same frames resident in HBM, CUDA events on the library's stream) for the roofline figure.
@@ -310,6 +321,7 @@ def run_ours(args):
         "e2e_u8_input": {"value": images / wall_u8, "unit": "images/s", "h2d_bytes_per_step": B * W * H, "ms_per_step": 1e3 * wall_u8 / args.steps,
                          "note": "supplementary: same call with SIFT_GPU_DTYPE_U8 host frames (identical results)"},
         "gpu_launches": int(launches),
+        "single_image_latency_ms": latency_ms,
         "roofline": {"bound": "hbm", "kernel": "pyramid+DoG stage (blur/DoG/decimation launches of one device pass)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
