@@ -101,6 +101,25 @@ def test_repeated_runs_replay_the_captured_stage_graph(built):
     g.close()
 
 
+def test_serial_context_and_long_batches_agree_with_the_pipelined_one(built):
+    """SIFT_GPU_FLAG_SERIAL (one pass at a time, what the bench's roofline is timed on) and a batch of many passes (every
+    slot reused several times, passes of 2, the last one ragged) must give the same results as the oracle."""
+    frames = [synth_frame(256, 192, s) for s in range(3)]
+    ref = [ol.Oracle(3, 3, 1.6, K, False).calculate(f) for f in frames]
+    order = [i % 3 for i in range(15)]
+    for flags in (0, capi.FLAG_SERIAL):
+        g = capi.SiftGpu(3, 3, 1.6, K, False, max_width=256, max_height=192, max_batch=2, flags=flags)
+        res = g.run([frames[i] for i in order])
+        assert len(res) == 15
+        for i, r in zip(order, res):
+            okp = ref[i]
+            assert r["status"] == 0 and r["kps"].size == okp["x"].size, (flags, i)
+            for f in ("x", "y", "octave", "index", "orientation", "filtered"):
+                assert np.array_equal(r["kps"][f], okp[f]), (flags, i, f)
+            assert np.array_equal(r["desc"], okp["desc"]), (flags, i)
+        g.close()
+
+
 def test_config1_parrot_defaults(built, parrot):
     """BASELINE config 1: example/parrot.jpg band 0, sigma 1.6, k sqrt2, 4 octaves, 3 DoGs, subpixel 0."""
     kp = full_compare(parrot, 4)
