@@ -56,7 +56,7 @@ class SparseFilterSort {
                 return;
             }
 #ifdef __GLIBCXX__
-            if ((zb - za) * 4 >= (size_t)(l - f)) {  // mostly unfiltered: cheaper to let libstdc++ run on the real thing
+            if ((zb - za) * 2 >= (size_t)(l - f)) {  // half unfiltered: cheaper to let libstdc++ run on the real thing
                 dense_segment(f, l, depth, za, zb);
                 return;
             }
@@ -83,7 +83,7 @@ class SparseFilterSort {
     }
 
 #ifdef __GLIBCXX__
-    // A segment in which at least a quarter of the elements is unfiltered is materialised as (filtered bit | id) words and
+    // A segment in which at least half of the elements is unfiltered is materialised as (filtered bit | id) words and
     // handed to libstdc++'s own __introsort_loop with the depth budget it has left at this point of the recursion — the
     // same code std::sort would be running here, so the permutation is the reference's by construction.
     void dense_segment(int64_t f, int64_t l, int depth, size_t za, size_t zb) {

@@ -180,3 +180,20 @@ def test_keypoint_overlay_matches_the_reference_geometry(built):
     # clipping: a square hanging over the border, a huge one, NaN orientation (flat window) — no crash, pixels stay inside
     img = draw([[2, 2, 0, 3.0, 30.0], [100, 80, 0, 500.0, 12.0], [60, 60, 0, 2.0, float("nan")]])
     assert img.shape == (160, 200, 3)
+
+
+def test_bench_reference_arm_prints_the_contract_line(built):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: one JSON line with the contract keys."""
+    import json
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
