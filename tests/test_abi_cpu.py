@@ -197,3 +197,31 @@ def test_bench_reference_arm_prints_the_contract_line(built):
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_sparse_sort_simulation_on_clustered_and_threshold_patterns(built):
+    """Survivors come in bursts (candidates are listed column by column), and the simulation switches to libstdc++'s own
+    loop once half of a segment is unfiltered: exercise bursts, densities around that switch and the depth-limit fallback."""
+    from sift_b200 import capi
+
+    rng = np.random.default_rng(7)
+    cases = 0
+    for n in (200, 1905, 5000, 30000, 139000):
+        for burst in (1, 3, 17, 200):
+            for density in (0.002, 0.014, 0.1, 0.24, 0.26, 0.45, 0.5, 0.55, 0.8, 0.99):
+                f = np.ones(n, np.uint8)
+                n_bursts = max(1, int(n * density / burst))
+                starts = rng.integers(0, max(1, n - burst), size=n_bursts)
+                for s0 in starts:
+                    f[s0:s0 + burst] = 0
+                full, fast = capi.sort_order(f), capi.sort_order_fast(f)
+                assert np.array_equal(full[: int((f == 0).sum())], fast), (n, burst, density)
+                cases += 1
+    # adversarial for median-of-three: sawtooth / organ-pipe layouts drive introsort towards its depth limit
+    for n in (1000, 4097, 20000):
+        i = np.arange(n)
+        for f in ((i % 3 == 0), (i < n // 2) ^ (i % 2 == 0), (np.minimum(i, n - 1 - i) % 5 < 2), (i * 2654435761 % 97 < 40)):
+            f = np.ascontiguousarray(f.astype(np.uint8))
+            assert np.array_equal(capi.sort_order(f)[: int((f == 0).sum())], capi.sort_order_fast(f)), n
+            cases += 1
+    assert cases >= 200
