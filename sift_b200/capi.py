@@ -135,6 +135,20 @@ def sort_order_fast(flags):
     return order[: n.value].copy()
 
 
+def results_to_dicts(res):
+    """Copies a ctypes Result array into plain numpy (the library's buffers are only valid until the next run)."""
+    out = []
+    for r in res:
+        if r.n:
+            kps = np.ctypeslib.as_array(C.cast(r.kps, C.POINTER(C.c_uint8)), (r.n * KP_DTYPE.itemsize,)).view(KP_DTYPE).copy()
+            desc = np.ctypeslib.as_array(r.desc, (r.n, 128)).copy()
+        else:
+            kps, desc = np.zeros(0, KP_DTYPE), np.zeros((0, 128), np.float32)
+        out.append(dict(status=r.status, kps=kps, desc=desc, n_candidates=r.n_candidates, n_survivors=r.n_survivors,
+                        out_width=r.out_width, out_height=r.out_height))
+    return out
+
+
 class SiftGpu:
     """One device context; mirrors the constructor of the reference's sift::Sift (sift.hpp:66-71)."""
 
@@ -192,16 +206,7 @@ class SiftGpu:
         rc, res = self.run_raw(descs, n)
         if rc != 0 and raise_on_error:
             raise self._err(rc)
-        out = []
-        for r in res:
-            if r.n:
-                kps = np.ctypeslib.as_array(C.cast(r.kps, C.POINTER(C.c_uint8)), (r.n * KP_DTYPE.itemsize,)).view(KP_DTYPE).copy()
-                desc = np.ctypeslib.as_array(r.desc, (r.n, 128)).copy()
-            else:
-                kps, desc = np.zeros(0, KP_DTYPE), np.zeros((0, 128), np.float32)
-            out.append(dict(status=r.status, kps=kps, desc=desc, n_candidates=r.n_candidates, n_survivors=r.n_survivors,
-                            out_width=r.out_width, out_height=r.out_height))
-        return out
+        return results_to_dicts(res)
 
     def timings(self):
         t = Timings()
@@ -273,3 +278,83 @@ class SiftGpu:
         if rc != 0:
             raise self._err(rc)
         return d
+
+
+# ---- nvJPEG front end (include/sift_gpu_jpeg.h, libsift_gpu_jpeg.so) --------------------------------------------
+class Jpeg(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t)]
+
+
+_jpeg_lib = None
+
+
+def load_jpeg():
+    global _jpeg_lib
+    if _jpeg_lib is None:
+        load()  # libsift_gpu.so first: the front end links against it
+        L = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsift_gpu_jpeg.so"))
+        L.sift_gpu_jpeg_create.restype = C.c_int
+        L.sift_gpu_jpeg_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.sift_gpu_jpeg_run.restype = C.c_int
+        L.sift_gpu_jpeg_run.argtypes = [C.c_void_p, C.POINTER(Jpeg), C.c_int, C.POINTER(Result)]
+        L.sift_gpu_jpeg_decoded.restype = C.c_int
+        L.sift_gpu_jpeg_decoded.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.sift_gpu_jpeg_last_error.restype = C.c_char_p
+        L.sift_gpu_jpeg_last_error.argtypes = [C.c_void_p]
+        L.sift_gpu_jpeg_destroy.restype = None
+        L.sift_gpu_jpeg_destroy.argtypes = [C.c_void_p]
+        _jpeg_lib = L
+    return _jpeg_lib
+
+
+JPEG_EXPORTED_SYMBOLS = ["sift_gpu_jpeg_create", "sift_gpu_jpeg_run", "sift_gpu_jpeg_decoded", "sift_gpu_jpeg_last_error",
+                         "sift_gpu_jpeg_destroy"]
+
+
+class SiftGpuJpeg:
+    """JPEG byte streams in, keypoints out: nvJPEG decode on the device, band 0 into the context `sift`."""
+
+    def __init__(self, sift, max_images):
+        self.L = load_jpeg()
+        self.sift = sift
+        h = C.c_void_p()
+        rc = self.L.sift_gpu_jpeg_create(sift.h, sift.prm.device, sift.prm.max_width, sift.prm.max_height, max_images, C.byref(h))
+        if rc != 0:
+            raise SiftGpuError(rc, self.L.sift_gpu_jpeg_last_error(None).decode())
+        self.h = h
+
+    def run(self, blobs):
+        n = len(blobs)
+        keep = [np.frombuffer(b, np.uint8) for b in blobs]
+        arr = (Jpeg * n)()
+        for i, a in enumerate(keep):
+            arr[i] = Jpeg(a.ctypes.data, a.size)
+        res = (Result * n)()
+        rc = self.L.sift_gpu_jpeg_run(self.h, arr, n, res)
+        if rc != 0:
+            raise SiftGpuError(rc, self.L.sift_gpu_jpeg_last_error(self.h).decode())
+        return results_to_dicts(res)
+
+    def decoded(self, i):
+        """Band 0 of image i of the last run, exactly the pixels the pipeline saw."""
+        w, h = C.c_int(), C.c_int()
+        rc = self.L.sift_gpu_jpeg_decoded(self.h, i, None, C.byref(w), C.byref(h))
+        if rc != 0:
+            raise SiftGpuError(rc, self.L.sift_gpu_jpeg_last_error(self.h).decode())
+        out = np.empty((h.value, w.value), np.uint8)
+        rc = self.L.sift_gpu_jpeg_decoded(self.h, i, out.ctypes.data, None, None)
+        if rc != 0:
+            raise SiftGpuError(rc, self.L.sift_gpu_jpeg_last_error(self.h).decode())
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sift_gpu_jpeg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+

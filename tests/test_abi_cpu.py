@@ -225,3 +225,27 @@ def test_sparse_sort_simulation_on_clustered_and_threshold_patterns(built):
             assert np.array_equal(capi.sort_order(f)[: int((f == 0).sum())], capi.sort_order_fast(f)), n
             cases += 1
     assert cases >= 200
+
+
+def test_jpeg_front_end_library_exports_its_header(built):
+    """include/sift_gpu_jpeg.h <-> libsift_gpu_jpeg.so: every declared entry point is exported (no compute without a GPU)."""
+    import ctypes
+    import re
+
+    from sift_b200 import capi
+
+    path = os.path.join(ROOT, "sift_b200", "libsift_gpu_jpeg.so")
+    if not os.path.exists(path):
+        pytest.skip("nvJPEG front end not built on this box")
+    declared = set(re.findall(r"\b(sift_gpu_jpeg_\w+)\s*\(", open(os.path.join(ROOT, "include", "sift_gpu_jpeg.h")).read()))
+    assert declared == set(capi.JPEG_EXPORTED_SYMBOLS)
+    capi.load()
+    lib = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    # without a device the constructor fails loudly
+    sift = None
+    with pytest.raises(capi.SiftGpuError):
+        sift = capi.SiftGpu(3, 3, max_width=64, max_height=64)
+    assert sift is None
+
