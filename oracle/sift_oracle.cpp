@@ -8,6 +8,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <set>
 #include <sstream>
 
@@ -20,8 +21,9 @@ namespace oracle {
 // (binary @0x41a900).  radius=(int)(3*sd+0.5) (>=1); tap = n*expf(s2*x*x) in fp32
 // with s2=(float)(-0.5/sf/sf), n=(float)(0.3989422804014327/sf); fp32 sequential sum,
 // scale=1/sum, tap*=scale.
-std::vector<float> gaussian_taps(float sigma, int* radius_out) {
-    const double std_dev = (double)sigma;
+std::vector<float> gaussian_taps(float sigma, int* radius_out) { return gaussian_taps_d((double)sigma, radius_out); }
+
+std::vector<float> gaussian_taps_d(double std_dev, int* radius_out) {
     if (!(std_dev >= 0.0))
         throw Precondition("Kernel1D::initGaussian(): Standard deviation must be >= 0.");
     std::vector<float> taps;
@@ -67,6 +69,35 @@ static void convolve_line_reflect(const float* src, long sstride, float* dst, lo
     }
 }
 
+// All lines of one pass over a strided 2-D array (axis 0: lines along x, axis 1: along y).  When x is
+// contiguous the y pass runs row-wise: acc[x] walks the same taps in the same order with the same separate
+// fp32 multiply and add as the per-line loop above, so every pixel sees identical arithmetic.
+void convolve_lines_reflect(const float* src, long ssx, long ssy, float* dst, long dsx, long dsy, int w, int h,
+                            const float* taps, int r, int axis) {
+    if (axis == 0) {
+        for (int y = 0; y < h; ++y) convolve_line_reflect(src + y * ssy, ssx, dst + y * dsy, dsx, w, taps, r);
+        return;
+    }
+    if (ssx != 1 || dsx != 1) {
+        for (int x = 0; x < w; ++x) convolve_line_reflect(src + x * ssx, ssy, dst + x * dsx, dsy, h, taps, r);
+        return;
+    }
+    std::vector<float> acc((size_t)w);
+    for (int y = 0; y < h; ++y) {
+        std::fill(acc.begin(), acc.end(), 0.0f);
+        for (int j = -r; j <= r; ++j) {
+            int s = y + j;
+            if (s < 0) s = -s;
+            if (s >= h) s = 2 * (h - 1) - s;
+            const float t = taps[r - j];
+            const float* row = src + (long)s * ssy;
+            float* a = acc.data();
+            for (int x = 0; x < w; ++x) a[x] += t * row[x];
+        }
+        std::memcpy(dst + (long)y * dsy, acc.data(), sizeof(float) * (size_t)w);
+    }
+}
+
 // algorithms.cpp:10-22: Kernel1D.initGaussian(sigma); separableConvolveX -> tmp; separableConvolveY.
 // Precondition: kernel longer than line when w <= r or h <= r.
 Image convolve_with_gauss(const Image& img, float sigma) {
@@ -74,12 +105,9 @@ Image convolve_with_gauss(const Image& img, float sigma) {
     std::vector<float> taps = gaussian_taps(sigma, &r);
     if (img.w < r + 1) throw Precondition("separableConvolveX(): kernel longer than line");
     Image tmp(img.w, img.h), res(img.w, img.h);
-    for (int y = 0; y < img.h; ++y)
-        convolve_line_reflect(&img.px[(size_t)y * img.w], 1, &tmp.px[(size_t)y * img.w], 1, img.w,
-                              taps.data(), r);
+    convolve_lines_reflect(img.px.data(), 1, img.w, tmp.px.data(), 1, img.w, img.w, img.h, taps.data(), r, 0);
     if (img.h < r + 1) throw Precondition("separableConvolveY(): kernel longer than line");
-    for (int x = 0; x < img.w; ++x)
-        convolve_line_reflect(&tmp.px[(size_t)x], img.w, &res.px[(size_t)x], img.w, img.h, taps.data(), r);
+    convolve_lines_reflect(tmp.px.data(), 1, img.w, res.px.data(), 1, img.w, img.w, img.h, taps.data(), r, 1);
     return res;
 }
 

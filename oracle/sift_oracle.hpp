@@ -30,6 +30,10 @@ struct Image {
 
 // --- alg:: primitives -------------------------------------------------------------------
 std::vector<float> gaussian_taps(float sigma, int* radius);           // Vigra Kernel1D::initGaussian
+std::vector<float> gaussian_taps_d(double std_dev, int* radius);      // same, with the double argument Vigra takes
+// every line of one separable pass (axis 0 = along x, 1 = along y) with Vigra's reflect border (A.2)
+void convolve_lines_reflect(const float* src, long ssx, long ssy, float* dst, long dsx, long dsy, int w, int h,
+                            const float* taps, int r, int axis);
 Image convolve_with_gauss(const Image& img, float sigma);             // algorithms.cpp:10-22
 Image resize_no_interpolation(const Image& src, int nw, int nh);      // Vigra resizeImageNoInterpolation
 std::vector<int> resize_index_map(int n_old, int n_new);              // the per-line index walk

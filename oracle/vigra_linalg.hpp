@@ -32,9 +32,11 @@ namespace la {
 
 // Strided 2-D view: (i, j) = row i, column j.
 struct MV {
-    float* p = nullptr;
-    long s0 = 0, s1 = 0;  // strides
-    long n0 = 0, n1 = 0;  // rows, columns
+    float* p;
+    long s0, s1;  // strides
+    long n0, n1;  // rows, columns
+    MV() : p(nullptr), s0(0), s1(0), n0(0), n1(0) {}
+    MV(float* p_, long s0_, long s1_, long n0_, long n1_) : p(p_), s0(s0_), s1(s1_), n0(n0_), n1(n1_) {}
     float& operator()(long i, long j) const { return p[i * s0 + j * s1]; }
     long rows() const { return n0; }
     long cols() const { return n1; }

@@ -28,13 +28,35 @@ def build():
 
 
 _lib = None
+_ref_libs = {}
+REF_DIR = os.path.join(_ROOT, "oracle", "_ref")
+
+
+def ref_available(fast=True):
+    """True when the reference's own sources were compiled here (oracle/_ref/, see oracle/Makefile)."""
+    return os.path.exists(os.path.join(REF_DIR, "libref_fast.so" if fast else "libref.so"))
+
+
+def ref_lib(fast=True):
+    """oracle/_ref/libref[_fast].so: /root/reference/{sift,algorithms}.cpp compiled unmodified against the Vigra
+    stand-in headers; same entry points as liboracle.so (oracle/ref_capi.cpp)."""
+    if fast not in _ref_libs:
+        path = os.path.join(REF_DIR, "libref_fast.so" if fast else "libref.so")
+        if not os.path.exists(path) and os.path.exists("/root/reference/sift.cpp"):
+            env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+            subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL, env=env)
+        _ref_libs[fast] = _bind(C.CDLL(path), ref=True)
+    return _ref_libs[fast]
 
 
 def lib():
     global _lib
-    if _lib is not None:
-        return _lib
-    L = C.CDLL(build())
+    if _lib is None:
+        _lib = _bind(C.CDLL(build()), ref=False)
+    return _lib
+
+
+def _bind(L, ref):
     L.oracle_create.restype = C.c_void_p
     L.oracle_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
     L.oracle_destroy.argtypes = [C.c_void_p]
@@ -59,13 +81,21 @@ def lib():
     L.oracle_get_keypoints.argtypes = [C.c_void_p, _u16p, _u16p, _u16p, _u16p, _f32p, _f32p, _u8p, _f32p, _i32p]
     L.oracle_format_results.restype = C.c_long
     L.oracle_format_results.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
-    L.oracle_gaussian_taps.restype = C.c_int
-    L.oracle_gaussian_taps.argtypes = [C.c_float, _f32p, C.c_int]
+    if not ref:
+        L.oracle_gaussian_taps.restype = C.c_int
+        L.oracle_gaussian_taps.argtypes = [C.c_float, _f32p, C.c_int]
+        L.oracle_resize_map.argtypes = [C.c_int, C.c_int, _i32p]
+        L.oracle_resize.restype = C.c_int
+        L.oracle_resize.argtypes = [_f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int]
+        L.oracle_inverse3.restype = C.c_int
+        L.oracle_inverse3.argtypes = [_f32p, _f32p]
+        L.oracle_linear_solve3.restype = C.c_int
+        L.oracle_linear_solve3.argtypes = [_f32p, _f32p, _f32p]
+    else:
+        L.oracle_flavour.restype = C.c_char_p
+        L.oracle_normalize.argtypes = [_f32p, C.c_int]
     L.oracle_convolve.restype = C.c_int
     L.oracle_convolve.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _f32p]
-    L.oracle_resize_map.argtypes = [C.c_int, C.c_int, _i32p]
-    L.oracle_resize.restype = C.c_int
-    L.oracle_resize.argtypes = [_f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int]
     L.oracle_reduce.restype = C.c_int
     L.oracle_reduce.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _f32p]
     L.oracle_increase.restype = C.c_int
@@ -74,10 +104,6 @@ def lib():
     L.oracle_extrema.restype = C.c_long
     L.oracle_extrema.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, _u16p, _u16p, C.c_long]
     L.oracle_eliminate.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, _u16p, _u16p, C.c_long, _u8p]
-    L.oracle_inverse3.restype = C.c_int
-    L.oracle_inverse3.argtypes = [_f32p, _f32p]
-    L.oracle_linear_solve3.restype = C.c_int
-    L.oracle_linear_solve3.argtypes = [_f32p, _f32p, _f32p]
     L.oracle_vertex_parabola.restype = C.c_float
     L.oracle_vertex_parabola.argtypes = [C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float]
     L.oracle_find_peaks.restype = C.c_int
@@ -86,7 +112,6 @@ def lib():
     L.oracle_gradient.argtypes = [_f32p, C.c_int, C.c_int, _f32p, _f32p]
     L.oracle_time_calculate.restype = C.c_double
     L.oracle_time_calculate.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.POINTER(C.c_int)]
-    _lib = L
     return L
 
 
@@ -98,8 +123,8 @@ class Oracle:
     """One reference-equivalent Sift object (ctor order of sift.hpp:66-71)."""
 
     def __init__(self, dogs_per_epoch=3, octaves=3, sigma=1.6, k=float(np.float32(np.sqrt(2.0))), subpixel=False,
-                 literal=False, strict=False):
-        self.L = lib()
+                 literal=False, strict=False, L=None):
+        self.L = L if L is not None else lib()
         self.dpe, self.octaves = dogs_per_epoch, octaves
         self.h = self.L.oracle_create(dogs_per_epoch, octaves, sigma, k, int(subpixel), int(literal), int(strict))
 
@@ -186,10 +211,10 @@ def gaussian_taps(sigma):
     return buf[: 2 * r + 1].copy(), r
 
 
-def convolve(img, sigma):
+def convolve(img, sigma, L=None):
     img = np.ascontiguousarray(img, np.float32)
     out = np.empty_like(img)
-    if lib().oracle_convolve(img, img.shape[1], img.shape[0], sigma, out) != 0:
+    if (L or lib()).oracle_convolve(img, img.shape[1], img.shape[0], sigma, out) != 0:
         raise OraclePrecondition("kernel longer than line")
     return out
 
@@ -200,47 +225,47 @@ def resize_map(n_old, n_new):
     return m
 
 
-def reduce(img, sigma):
+def reduce(img, sigma, L=None):
     img = np.ascontiguousarray(img, np.float32)
     h, w = img.shape
     out = np.empty(((h + 1) // 2, (w + 1) // 2), np.float32)
-    if lib().oracle_reduce(img, w, h, sigma, out) != 0:
+    if (L or lib()).oracle_reduce(img, w, h, sigma, out) != 0:
         raise OraclePrecondition("reduce")
     return out
 
 
-def increase(img, sigma):
+def increase(img, sigma, L=None):
     img = np.ascontiguousarray(img, np.float32)
     h, w = img.shape
     out = np.empty((2 * h, 2 * w), np.float32)
-    if lib().oracle_increase(img, w, h, sigma, out) != 0:
+    if (L or lib()).oracle_increase(img, w, h, sigma, out) != 0:
         raise OraclePrecondition("increase")
     return out
 
 
-def dog(lower, higher):
+def dog(lower, higher, L=None):
     lower = np.ascontiguousarray(lower, np.float32)
     higher = np.ascontiguousarray(higher, np.float32)
     out = np.empty_like(lower)
-    lib().oracle_dog(lower, higher, lower.size, out)
+    (L or lib()).oracle_dog(lower, higher, lower.size, out)
     return out
 
 
-def extrema(d0, d1, d2):
+def extrema(d0, d1, d2, L=None):
     d0, d1, d2 = (np.ascontiguousarray(a, np.float32) for a in (d0, d1, d2))
     h, w = d1.shape
     cap = w * h
     xs, ys = np.zeros(cap, np.uint16), np.zeros(cap, np.uint16)
-    n = lib().oracle_extrema(d0, d1, d2, w, h, xs, ys, cap)
+    n = (L or lib()).oracle_extrema(d0, d1, d2, w, h, xs, ys, cap)
     return xs[:n].copy(), ys[:n].copy()
 
 
-def eliminate(d0, d1, d2, xs, ys):
+def eliminate(d0, d1, d2, xs, ys, L=None):
     d0, d1, d2 = (np.ascontiguousarray(a, np.float32) for a in (d0, d1, d2))
     h, w = d1.shape
     xs, ys = np.ascontiguousarray(xs, np.uint16), np.ascontiguousarray(ys, np.uint16)
     f = np.zeros(xs.size, np.uint8)
-    lib().oracle_eliminate(d0, d1, d2, w, h, xs, ys, xs.size, f)
+    (L or lib()).oracle_eliminate(d0, d1, d2, w, h, xs, ys, xs.size, f)
     return f
 
 
@@ -259,26 +284,26 @@ def linear_solve3(a, b):
     return bool(ok), out
 
 
-def vertex_parabola(lx, ly, px, py, rx, ry):
-    return lib().oracle_vertex_parabola(lx, ly, px, py, rx, ry)
+def vertex_parabola(lx, ly, px, py, rx, ry, L=None):
+    return (L or lib()).oracle_vertex_parabola(lx, ly, px, py, rx, ry)
 
 
-def find_peaks(histo):
+def find_peaks(histo, L=None):
     histo = np.ascontiguousarray(histo, np.float32)
     out = np.zeros(36, np.float32)
-    n = lib().oracle_find_peaks(histo, out)
+    n = (L or lib()).oracle_find_peaks(histo, out)
     return out[:n].copy()
 
 
-def sort_order(flags):
+def sort_order(flags, L=None):
     flags = np.ascontiguousarray(flags, np.uint8)
     order = np.zeros(flags.size, np.uint32)
-    lib().oracle_sort_order(flags, flags.size, order)
+    (L or lib()).oracle_sort_order(flags, flags.size, order)
     return order
 
 
-def gradient(img):
+def gradient(img, L=None):
     img = np.ascontiguousarray(img, np.float32)
     mag, ori = np.empty_like(img), np.empty_like(img)
-    lib().oracle_gradient(img, img.shape[1], img.shape[0], mag, ori)
+    (L or lib()).oracle_gradient(img, img.shape[1], img.shape[0], mag, ori)
     return mag, ori
