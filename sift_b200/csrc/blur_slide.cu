@@ -1,0 +1,492 @@
+// Sliding-accumulator Gaussian blur: alg::convolveWithGauss (reference algorithms.cpp:10-22) with the DoG of
+// algorithms.cpp:52-64 fused into the epilogue, for the large levels of the pyramid.
+//
+// Every warp is an independent pipeline over a 64-column strip of a row segment (no CTA-wide barrier):
+//   * TMA (cp.async.bulk.tensor.3d, mbarrier expect_tx) stages 8-row boxes of SWW = 96 or 128 columns two chunks
+//     ahead into a ring of three stages; rows above/below the image arrive as 1-row boxes at their reflected index,
+//     columns left/right of it are zero-filled by TMA and patched by a smem -> smem mirror on edge strips;
+//   * row pass: lane = 4 adjacent columns x 4 rows, float4 window loads (the lanes of a quarter-warp read 128 contiguous
+//     bytes: conflict-free for any row pitch), results to an 8-row buffer `mid`;
+//   * column pass: lane = 2 adjacent columns.  The 2R+1 output rows a source row contributes to live in 2R+1 float2
+//     ACCUMULATORS IN REGISTERS: each new row-filtered line h(v) is loaded once (one LDS.64) and scattered into them
+//     (acc[yo] += tk[v - yo + R] * h(v)); the accumulator whose last tap this was is complete and leaves through the
+//     epilogue (dst, and dog = 128 + (dst - src); the row pass parks the centre pixels src in a small buffer `cen`).  An output row therefore
+//     receives its taps in ascending source order exactly like the reference's line loop, there is no ring of
+//     row-filtered lines to re-read, no vertical halo is recomputed inside a segment, and the 2R+1 operations of a step
+//     are independent of each other.  The sums move down one register per step; the FFMA2 that adds a tap writes its
+//     result one place lower than it read it, so the shift is free and every step runs the same code.
+//
+// Arithmetic: exact mode = packed multiply, then the add as fma(m, 1, acc) with a run-time 1 (ptxas contracts a packed
+// multiply feeding a packed add into one FFMA2 even under -fmad=false; see pyramid.cu) -> bit-identical to the
+// reference's mulss/addss; FMA mode = one FFMA2 per tap pair.  Radii are instantiated for a few R; a blur of radius
+// r runs on the smallest R >= r with zero taps added symmetrically (acc + 0*v == acc for the finite values of an image).
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace siftgpu {
+
+__host__ __device__ __forceinline__ int sl_reflect(int v, int n) {
+    if (v < 0) v = -v;
+    if (v >= n) v = 2 * (n - 1) - v;
+    v = v < 0 ? 0 : v;            // only reachable for padding rows/columns that no valid output reads
+    return v >= n ? n - 1 : v;
+}
+
+template <int R, bool DOG>
+struct SL {
+    static constexpr int WC = 64;                     // output columns per warp
+    static constexpr int CH = 8;                      // rows per chunk = rows per TMA stage
+    static constexpr int NWARP = 2;                   // warps per CTA (adjacent strips)
+    static constexpr int RPAD = (R + 3) & ~3;
+    static constexpr int OFF = RPAD - R;
+    static constexpr int SWW = (WC + 2 * RPAD <= 96) ? 96 : 128;   // staged floats per row: a multiple of 128 B, so that the 1-row boxes
+                                                                   // of reflected rows land on 128-B aligned shared-memory addresses
+    static constexpr int NACC = 2 * R;                // partial sums carried from step to step (the 2R+1-th is born and the oldest leaves in a step)
+    static constexpr int NB = DOG ? (R + CH - 1) / CH + 1 : 0;   // 8-row blocks of centre pixels kept for the DoG: rows v - R .. end of the chunk
+    static constexpr int MAX_AHEAD = 4;               // chunks in flight: a launch parameter (SlideArgs::ahead), stages = ahead + 1
+    static constexpr int MW = 64;                     // row pitch of `mid` and `cen`
+    static constexpr int STAGE_FLOATS = CH * SWW;
+    static constexpr int MID_FLOATS = CH * MW;
+    static constexpr int CEN_FLOATS = NB * CH * MW;
+    static constexpr int NW = 4 + 2 * RPAD;           // row-pass window of one group of 4 outputs
+    static constexpr int warp_floats(int nstg) { return nstg * STAGE_FLOATS + MID_FLOATS + CEN_FLOATS; }
+    static constexpr size_t smem(int nstg) { return sizeof(float) * (size_t)(NWARP * warp_floats(nstg)) + NWARP * (MAX_AHEAD + 1) * sizeof(uint64_t); }
+    static_assert(WC + 2 * RPAD <= SWW && (SWW * 4) % 128 == 0 && (STAGE_FLOATS * 4) % 128 == 0 && ((MID_FLOATS + CEN_FLOATS) * 4) % 128 == 0,
+                  "TMA destinations must stay 128-B aligned");
+};
+
+template <int R>
+struct SlideTaps {        // tk[j] = tap applied to source index x - R + j; symmetric (tk[j] == tk[2R - j], checked on the host)
+    float tk[R + 1];      // j <= R; the column pass uses them as (tk, tk): ptxas folds that into a scalar-broadcast FFMA2 operand
+    float one;            // 1 as a run-time value (see header)
+    float2 pe[R];         // (tk[2m], tk[2m+1])
+    float2 po[R];         // (tk[2m+1], tk[2m+2])
+};
+
+struct SlideArgs {
+    BlurArgs a;
+    int seg;              // output rows per CTA
+    int ahead;            // chunks in flight per warp (stages = ahead + 1)
+};
+
+// one output of the row pass: sum over j of tk[j] * wv[BASE + j], ascending j
+template <int R, bool FMA, int BASE, int NWV>
+__device__ __forceinline__ float sl_row_output(const float (&wv)[NWV], const SlideTaps<R>& tp) {
+    const float tk0 = tp.tk[0];
+    if (FMA) {
+        float2 acc2;
+        if (BASE % 2 == 0) {
+            acc2 = __fmul2_rn(tp.pe[0], make_float2(wv[BASE], wv[BASE + 1]));
+#pragma unroll
+            for (int m = 1; m < R; ++m) acc2 = __ffma2_rn(tp.pe[m], make_float2(wv[BASE + 2 * m], wv[BASE + 2 * m + 1]), acc2);
+            acc2.x = fmaf(tk0, wv[BASE + 2 * R], acc2.x);   // tk[2R] == tk[0]
+        } else {
+            acc2 = __fmul2_rn(tp.po[0], make_float2(wv[BASE + 1], wv[BASE + 2]));
+#pragma unroll
+            for (int m = 1; m < R; ++m) acc2 = __ffma2_rn(tp.po[m], make_float2(wv[BASE + 2 * m + 1], wv[BASE + 2 * m + 2]), acc2);
+            acc2.x = fmaf(tk0, wv[BASE], acc2.x);
+        }
+        return acc2.x + acc2.y;
+    } else {
+        float acc;
+        if (BASE % 2 == 0) {
+            const float2 m0 = __fmul2_rn(tp.pe[0], make_float2(wv[BASE], wv[BASE + 1]));
+            acc = __fadd_rn(m0.x, m0.y);
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+                const float2 pm = __fmul2_rn(tp.pe[m], make_float2(wv[BASE + 2 * m], wv[BASE + 2 * m + 1]));
+                acc = __fadd_rn(__fadd_rn(acc, pm.x), pm.y);
+            }
+            acc = __fadd_rn(acc, __fmul_rn(tk0, wv[BASE + 2 * R]));
+        } else {
+            acc = __fmul_rn(tk0, wv[BASE]);
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const float2 pm = __fmul2_rn(tp.po[m], make_float2(wv[BASE + 2 * m + 1], wv[BASE + 2 * m + 2]));
+                acc = __fadd_rn(__fadd_rn(acc, pm.x), pm.y);
+            }
+        }
+        return acc;
+    }
+}
+
+// Reflect patch of one staged chunk (edge strips only): staged column c holds x = xs - rpad + c; TMA zero-filled what lies
+// outside the image; columns -1..-r and w..w+r-1 get their mirrored pixels, which are staged in the same row.
+__device__ __noinline__ void sl_patch_columns(float* st, int rows, int w, int xs, int rpad, int r, int sww, int lane) {
+    const int n = 2 * r;
+    for (int e = lane; e < rows * n; e += 32) {
+        const int rr = e / n, k = e - rr * n;
+        const int gx = k < r ? -1 - k : w + (k - r);
+        const int c = gx - (xs - rpad);
+        const int cs = sl_reflect(gx, w) - (xs - rpad);
+        if (c >= 0 && c < sww && cs >= 0 && cs < sww) st[rr * sww + c] = st[rr * sww + cs];
+    }
+    tma::fence_proxy_async();  // generic-proxy writes above vs. the next TMA write into this stage
+    __syncwarp();
+}
+
+// shared-memory addresses as 32-bit values (one conversion per kernel instead of one per use)
+__device__ __forceinline__ void sl_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sl_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+__device__ __forceinline__ void sl_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SL_DONE;\n"
+        "bra SL_WAIT;\n"
+        "SL_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// a chunk with rows above/below the image: eight 1-row boxes at the reflected row indices
+__device__ __noinline__ void sl_issue_reflected(uint32_t dst, uint32_t bar, const CUtensorMap* map1, int x, int v0, int h, int b, int sww) {
+#pragma unroll 1
+    for (int rr = 0; rr < 8; ++rr) sl_load_3d(dst + rr * sww * 4, map1, bar, x, sl_reflect(v0 + rr, h), b);
+}
+__device__ __forceinline__ void sl_issue_chunk(uint32_t dst, uint32_t bar, const CUtensorMap* map8, const CUtensorMap* map1, int x, int v0, int h,
+                                               int b, int sww) {
+    sl_expect_tx(bar, 8 * sww * (int)sizeof(float));
+    if (v0 >= 0 && v0 + 8 <= h) sl_load_3d(dst, map8, bar, x, v0, b);
+    else sl_issue_reflected(dst, bar, map1, x, v0, h, b, sww);
+}
+
+__device__ __forceinline__ void sl_store2_if(void* p, float2 v, uint32_t ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.u32 q, %3, 0;\n"
+        "@q st.global.v2.f32 [%0], {%1, %2};\n"
+        "}\n" ::"l"(p), "f"(v.x), "f"(v.y), "r"(ok)
+        : "memory");
+}
+
+// One step of the column pass = one new row-filtered line h (this lane's two columns).  acc[k] holds the partial sum of
+// output row v - R + k, which has received the taps of source rows up to v - 1.  The line contributes tap 2R - k to acc[k];
+// acc[0] is then complete, everything else moves down one place (the FFMA2 writes acc[k] from acc[k + 1], so the shift
+// costs nothing) and a new sum is born at the top.  Every output receives its taps in ascending source order.
+template <int R, bool FMA>
+__device__ __forceinline__ float2 sl_col_step(float2 (&acc)[2 * R], const float2 h, const float (&tk)[R + 1], const float one) {
+    auto tap = [&](int j) { return tk[j <= R ? j : 2 * R - j]; };
+    auto fma2 = [&](float t, float2 a) {
+        if (FMA) return __ffma2_rn(make_float2(t, t), h, a);
+        return __ffma2_rn(__fmul2_rn(make_float2(t, t), h), make_float2(one, one), a);
+    };
+    const float2 res = fma2(tap(2 * R), acc[0]);
+#pragma unroll
+    for (int k = 0; k + 1 < 2 * R; ++k) acc[k] = fma2(tap(2 * R - 1 - k), acc[k + 1]);
+    acc[2 * R - 1] = __fmul2_rn(make_float2(tk[0], tk[0]), h);
+    return res;
+}
+
+// MODE: 0 = dst only, 1 = dst + DoG, 2 = DoG only.  CHECK: steps outside [2R, n_virtual) must not store (first and last chunks).
+template <int R, bool FMA, int MODE, bool CHECK>
+__device__ __forceinline__ void sl_col_chunk(float2 (&acc)[2 * R], const float* mid_lane, const float* const (&cb)[SL<R, MODE != 0>::NB + 1],
+                                             const float (&tk)[R + 1], const float one, char*& row, const size_t pitch_bytes, const ptrdiff_t dog_delta,
+                                             const bool active, const int t0, const int n_virtual) {
+    using C = SL<R, MODE != 0>;
+#pragma unroll
+    for (int r = 0; r < C::CH; ++r) {
+        const float2 h = *reinterpret_cast<const float2*>(mid_lane + r * C::MW);
+        float2 lo = make_float2(0.0f, 0.0f);
+        if (MODE != 0) {   // centre pixels of output row v - R: (R - r) rows back -> block q back, row rr of it
+            const int back = R - r;
+            const int q = back > 0 ? (back + C::CH - 1) / C::CH : 0;
+            const int rr = r - R + C::CH * q;
+            lo = *reinterpret_cast<const float2*>(cb[q] + rr * C::MW);
+        }
+        const float2 res = sl_col_step<R, FMA>(acc, h, tk, one);
+        // predicated stores, no branch
+        const uint32_t ok = (CHECK ? (active && t0 + r >= 2 * R && t0 + r < n_virtual) : active) ? 1u : 0u;
+        if (MODE != 2) sl_store2_if(row, res, ok);
+        if (MODE != 0) {
+            // higher - lower, then 128 + dif (algorithms.cpp:58-60)
+            const float2 dif = __fadd2_rn(res, make_float2(-lo.x, -lo.y));
+            sl_store2_if(row + (MODE == 1 ? dog_delta : 0), __fadd2_rn(make_float2(128.0f, 128.0f), dif), ok);
+        }
+        row += pitch_bytes;
+    }
+}
+
+template <int R, bool FMA, int MODE>
+__global__ void __launch_bounds__(64) blur_slide_kernel(const __grid_constant__ CUtensorMap map8, const __grid_constant__ CUtensorMap map1,
+                                                        const SlideArgs sa, const SlideTaps<R> taps) {
+    constexpr bool DOG = MODE != 0;
+    using C = SL<R, DOG>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nstg = sa.ahead + 1;
+    const int warp_floats = nstg * C::STAGE_FLOATS + C::MID_FLOATS + C::CEN_FLOATS;
+    float* stage = reinterpret_cast<float*>(smem_raw) + warp * warp_floats;          // [nstg][CH][SWW]
+    float* mid = stage + nstg * C::STAGE_FLOATS;                                     // [CH][MW] row-filtered lines of the current chunk
+    float* cen = mid + C::MID_FLOATS;                                               // [NB][CH][MW] centre pixels of the last rows (DoG)
+    const uint32_t stage_u = tma::smem_u32(stage);
+    const uint32_t full_u = tma::smem_u32(reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + C::NWARP * warp_floats) + warp * (C::MAX_AHEAD + 1));
+
+    const BlurArgs& a = sa.a;
+    const int b = blockIdx.z + a.z0;
+    const int w = a.w, h = a.h;
+    const int xs = (blockIdx.x * C::NWARP + warp) * C::WC;
+    if (xs >= w) return;                                    // warps are independent: no barrier below
+    const int y0 = blockIdx.y * sa.seg;
+    const int y1 = min(y0 + sa.seg, h);
+    const int n_virtual = (y1 - y0) + 2 * R;                // virtual rows y0 - R .. y1 + R - 1 feed this segment
+    const int n_chunks = (n_virtual + C::CH - 1) / C::CH;
+    const int v_first = y0 - R;
+    const bool edge = (xs - C::RPAD < 0) || (xs - C::RPAD + C::SWW > w);
+
+    if (lane == 0) {
+        tma::prefetch_map(&map8);
+        for (int s = 0; s < nstg; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_u + 8 * s) : "memory");
+        tma::fence_barrier_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < nstg && i < n_chunks; ++i)
+            sl_issue_chunk(stage_u + i * C::STAGE_FLOATS * 4, full_u + 8 * i, &map8, &map1, xs - C::RPAD, v_first + i * C::CH, h, b, C::SWW);
+    }
+
+    float tk[R + 1];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) tk[j] = taps.tk[j];
+    const float one = taps.one;
+
+    // row pass: lane = (row parity, column group)
+    const int cg = lane & 15, rsub = lane >> 4;
+    // column pass: columns xs + 2*lane, +1 (for an odd width the second column lies in the row's padding: pitch % 32 == 0)
+    const int x = xs + 2 * lane;
+    const bool active = x < w;
+    // address of output row (t - 2R) of the segment at the lane's columns: it starts 2R rows above the segment and moves down one
+    // row per step; stores only happen once t >= 2R.  MODE 0/1: dst (dog = dst + dog_delta), MODE 2: dog.
+    const float* obase = MODE == 2 ? a.dog + (size_t)b * a.dog_stride : a.dst + (size_t)b * a.dst_stride;
+    const int opitch = MODE == 2 ? a.dog_pitch : a.dst_pitch;
+    const size_t pitch_bytes = (size_t)opitch * sizeof(float);
+    char* row = reinterpret_cast<char*>(const_cast<float*>(obase)) + ((ptrdiff_t)(y0 - 2 * R) * opitch + (active ? x : 0)) * (ptrdiff_t)sizeof(float);
+    const ptrdiff_t dog_delta =
+        MODE == 1 ? (reinterpret_cast<const char*>(a.dog + (size_t)b * a.dog_stride) - reinterpret_cast<const char*>(a.dst + (size_t)b * a.dst_stride)) : 0;
+
+    float2 acc[C::NACC];
+#pragma unroll
+    for (int k = 0; k < C::NACC; ++k) acc[k] = make_float2(0.0f, 0.0f);
+
+    int s = 0;                 // stage of chunk i, its mbarrier phase parity
+    uint32_t parity = 0;
+    int cur = 0;               // block of `cen` the current chunk's centre pixels go to
+    const float* const mid_lane = mid + 2 * lane;
+#pragma unroll 1
+    for (int i = 0; i < n_chunks; ++i) {
+        float* const st = stage + s * C::STAGE_FLOATS;
+        sl_wait(full_u + 8 * s, parity);
+        if (edge) sl_patch_columns(st, C::CH, w, xs, C::RPAD, R, C::SWW, lane);
+
+        // blocks of `cen`: cb[q] = the block q chunks back (cb[0] = this chunk's)
+        const float* cb[C::NB + 1];
+#pragma unroll
+        for (int q = 0; q < C::NB; ++q) {
+            int blk = cur - q;
+            blk = blk < 0 ? blk + C::NB : blk;
+            cb[q] = cen + blk * (C::CH * C::MW) + 2 * lane;
+        }
+        cb[C::NB] = nullptr;
+
+        // ---- row pass: lane = 4 adjacent columns x rows rsub, rsub+2, rsub+4, rsub+6 (a quarter-warp reads 128 contiguous bytes).
+        // The window of the next row is loaded before the current one is filtered (two register sets), so the shared-memory
+        // latency of one row hides behind the arithmetic of the other.
+        {
+            float wv[2][C::NW];
+            auto load_window = [&](float (&dstw)[C::NW], int rw) {
+                const float* srow = st + rw * C::SWW + 4 * cg;
+#pragma unroll
+                for (int k = 0; k < C::NW / 4; ++k) {
+                    const float4 f = *reinterpret_cast<const float4*>(srow + 4 * k);
+                    dstw[4 * k] = f.x; dstw[4 * k + 1] = f.y; dstw[4 * k + 2] = f.z; dstw[4 * k + 3] = f.w;
+                }
+            };
+            load_window(wv[0], rsub);
+#pragma unroll
+            for (int q = 0; q < C::CH / 2; ++q) {
+                const int rw = rsub + 2 * q;
+                if (q + 1 < C::CH / 2) load_window(wv[(q + 1) & 1], rw + 2);
+                const float (&wq)[C::NW] = wv[q & 1];
+                if (DOG)   // the four centre pixels are window elements RPAD .. RPAD+3
+                    *reinterpret_cast<float4*>(cen + cur * (C::CH * C::MW) + rw * C::MW + 4 * cg) =
+                        make_float4(wq[C::RPAD], wq[C::RPAD + 1], wq[C::RPAD + 2], wq[C::RPAD + 3]);
+                float4 o4;
+                o4.x = sl_row_output<R, FMA, C::OFF + 0>(wq, taps);
+                o4.y = sl_row_output<R, FMA, C::OFF + 1>(wq, taps);
+                o4.z = sl_row_output<R, FMA, C::OFF + 2>(wq, taps);
+                o4.w = sl_row_output<R, FMA, C::OFF + 3>(wq, taps);
+                *reinterpret_cast<float4*>(mid + rw * C::MW + 4 * cg) = o4;
+            }
+        }
+        __syncwarp();   // mid / cen rows visible to the whole warp; every lane is done with stage s
+        // the row pass was the stage's only reader (the DoG's centre pixels went to `cen`): refill it with chunk i + nstg right away
+        if (lane == 0 && i + nstg < n_chunks)
+            sl_issue_chunk(stage_u + s * C::STAGE_FLOATS * 4, full_u + 8 * s, &map8, &map1, xs - C::RPAD, v_first + (i + nstg) * C::CH, h, b, C::SWW);
+
+        // ---- column pass: 8 steps ----
+        const int t0 = i * C::CH;
+        if (t0 >= 2 * R && t0 + C::CH <= n_virtual)
+            sl_col_chunk<R, FMA, MODE, false>(acc, mid_lane, cb, tk, one, row, pitch_bytes, dog_delta, active, t0, n_virtual);
+        else
+            sl_col_chunk<R, FMA, MODE, true>(acc, mid_lane, cb, tk, one, row, pitch_bytes, dog_delta, active, t0, n_virtual);
+        __syncwarp();   // every lane is done with mid
+        if (DOG) cur = cur + 1 == C::NB ? 0 : cur + 1;
+        if (++s == nstg) { s = 0; parity ^= 1u; }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+static constexpr int kSlideRadii[] = {3, 5, 7, 10, 14, 19, 27};
+
+int slide_radius_for(int r) {
+    for (int R : kSlideRadii)
+        if (r <= R) return R;
+    return 0;
+}
+
+template <int R>
+static int slide_box_width_r(bool dog) { return dog ? SL<R, true>::SWW : SL<R, false>::SWW; }
+static_assert(SL<10, true>::SWW == SL<10, false>::SWW, "the staged width must not depend on the mode");
+
+int slide_box_width(int r) {   // same for DOG and plain (SWW does not depend on it)
+    switch (slide_radius_for(r)) {
+        case 3: return slide_box_width_r<3>(true);
+        case 5: return slide_box_width_r<5>(true);
+        case 7: return slide_box_width_r<7>(true);
+        case 10: return slide_box_width_r<10>(true);
+        case 14: return slide_box_width_r<14>(true);
+        case 19: return slide_box_width_r<19>(true);
+        case 27: return slide_box_width_r<27>(true);
+        default: return 0;
+    }
+}
+
+struct SlideDevInfo { bool ready = false; int n_sm = 148; int ahead = 1; int cps[8][2][3] = {}; };   // [radius index][fma][mode]
+static int slide_ahead() {
+    static const int v = [] { const char* e = getenv("SIFT_GPU_SLIDE_AHEAD"); int a = e ? atoi(e) : 1; return a < 1 ? 1 : (a > 4 ? 4 : a); }();
+    return v;
+}
+static SlideDevInfo g_slide_dev[64];
+
+template <int R, bool FMA, int MODE>
+static int slide_prepare_one(int* cps) {
+    using C = SL<R, MODE != 0>;
+    const size_t smem = C::smem(slide_ahead() + 1);
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_slide_kernel<R, FMA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    SIFT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_slide_kernel<R, FMA, MODE>, C::NWARP * 32, smem));
+    *cps = n > 0 ? n : 1;
+    return 0;
+}
+template <int R>
+static int slide_prepare_r(SlideDevInfo& d, int idx) {
+    int rc;
+    if ((rc = slide_prepare_one<R, false, 0>(&d.cps[idx][0][0])) || (rc = slide_prepare_one<R, false, 1>(&d.cps[idx][0][1])) ||
+        (rc = slide_prepare_one<R, false, 2>(&d.cps[idx][0][2])) || (rc = slide_prepare_one<R, true, 0>(&d.cps[idx][1][0])) ||
+        (rc = slide_prepare_one<R, true, 1>(&d.cps[idx][1][1])) || (rc = slide_prepare_one<R, true, 2>(&d.cps[idx][1][2])))
+        return rc;
+    return 0;
+}
+
+// Per-device set-up (function attributes are per device): called from sift_gpu_create after cudaSetDevice.
+int slide_prepare_device() {
+    int dev = 0;
+    SIFT_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return 0;
+    SlideDevInfo& d = g_slide_dev[dev];
+    if (d.ready) return 0;
+    if (cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.n_sm <= 0) d.n_sm = 148;
+    int rc;
+    if ((rc = slide_prepare_r<3>(d, 0)) || (rc = slide_prepare_r<5>(d, 1)) || (rc = slide_prepare_r<7>(d, 2)) || (rc = slide_prepare_r<10>(d, 3)) ||
+        (rc = slide_prepare_r<14>(d, 4)) || (rc = slide_prepare_r<19>(d, 5)) || (rc = slide_prepare_r<27>(d, 6)))
+        return rc;
+    d.ready = true;
+    return 0;
+}
+
+template <int R>
+static int launch_slide_r(const BlurArgs& a, int batch, bool fma, int idx, cudaStream_t s) {
+    using C = SL<R, true>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !g_slide_dev[dev].ready) {
+        const int rc = slide_prepare_device();
+        if (rc) return rc;
+    }
+    const SlideDevInfo& d = g_slide_dev[dev < 64 && dev >= 0 ? dev : 0];
+    const int mode = a.dog ? (a.dst ? 1 : 2) : 0;
+    if (!a.dog && !a.dst) return -1;
+    if (mode == 1 && a.dst_pitch != a.dog_pitch) return -1;   // one row pointer serves both outputs
+    // taps for radius R: tk[j], j = 0..2R, zero outside the real radius; the kernel relies on their symmetry
+    const int r = a.r, pad = R - r;
+    float tk[2 * R + 1];
+    for (int j = 0; j <= 2 * R; ++j) tk[j] = (j >= pad && j <= pad + 2 * r) ? a.taps_host[2 * r - (j - pad)] : 0.0f;
+    for (int j = 0; j < R; ++j)
+        if (tk[j] != tk[2 * R - j]) return -1;   // not a symmetric kernel: another implementation takes it
+    SlideTaps<R> tp;
+    tp.one = 1.0f;
+    for (int j = 0; j <= R; ++j) tp.tk[j] = tk[j];
+    for (int m = 0; m < R; ++m) {
+        tp.pe[m] = make_float2(tk[2 * m], tk[2 * m + 1]);
+        tp.po[m] = make_float2(tk[2 * m + 1], tk[2 * m + 2]);
+    }
+    SlideArgs sa;
+    sa.a = a;
+    // Rows per CTA: more segments = more parallelism but 2R extra rows to stage, row-filter and scatter per segment; fewer
+    // segments = less overhead but a ragged last wave.  Pick the count with the best (last-wave fill) / (overhead).
+    const int strips = (a.w + C::NWARP * C::WC - 1) / (C::NWARP * C::WC);
+    const int cps = d.cps[idx][fma ? 1 : 0][mode];
+    static const bool use_share = [] { const char* e = getenv("SIFT_GPU_SLIDE_SHARE"); return e ? atoi(e) != 0 : true; }();
+    const double slots = (double)d.n_sm * cps / (use_share && a.share > 1 ? a.share : 1);
+    int seg = a.h;
+    double best = -1.0;
+    for (int nseg = 1; nseg <= (a.h + 15) / 16; ++nseg) {
+        const int sg = ((a.h + nseg - 1) / nseg + C::CH - 1) / C::CH * C::CH;
+        const int real_segs = (a.h + sg - 1) / sg;
+        const double tiles = (double)strips * real_segs * batch;
+        const double waves = std::ceil(tiles / slots);
+        const double fill = tiles / (waves * slots);
+        const double overhead = (double)(sg + 2 * R + C::CH) / sg;
+        const double score = fill / overhead;
+        if (score > best + 1e-9) { best = score; seg = sg; }
+    }
+    sa.seg = seg;
+    sa.ahead = slide_ahead();
+    dim3 grid(strips, (a.h + seg - 1) / seg, batch);
+#define SL_LAUNCH(F, M) blur_slide_kernel<R, F, M><<<grid, C::NWARP * 32, SL<R, M != 0>::smem(sa.ahead + 1), s>>>(a.map[0], a.map[1], sa, tp)
+    if (fma) { if (mode == 0) SL_LAUNCH(true, 0); else if (mode == 1) SL_LAUNCH(true, 1); else SL_LAUNCH(true, 2); }
+    else { if (mode == 0) SL_LAUNCH(false, 0); else if (mode == 1) SL_LAUNCH(false, 1); else SL_LAUNCH(false, 2); }
+#undef SL_LAUNCH
+    SIFT_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// returns -1 when the launch does not qualify (decimation, no TMA descriptors, small level, radius above 27)
+int launch_slide(const BlurArgs& a, int batch, bool fma, cudaStream_t s) {
+    static const bool off = getenv("SIFT_GPU_NO_SLIDE") != nullptr;
+    if (off || a.sel_x || !a.map || !a.taps_host || a.w < 32 || a.h < 16) return -1;
+    switch (slide_radius_for(a.r)) {
+        case 3: return launch_slide_r<3>(a, batch, fma, 0, s);
+        case 5: return launch_slide_r<5>(a, batch, fma, 1, s);
+        case 7: return launch_slide_r<7>(a, batch, fma, 2, s);
+        case 10: return launch_slide_r<10>(a, batch, fma, 3, s);
+        case 14: return launch_slide_r<14>(a, batch, fma, 4, s);
+        case 19: return launch_slide_r<19>(a, batch, fma, 5, s);
+        case 27: return launch_slide_r<27>(a, batch, fma, 6, s);
+        default: return -1;
+    }
+}
+
+}  // namespace siftgpu

@@ -75,7 +75,8 @@ struct BlurArgs {
     int r;
     const int* sel_x; // decimation: destination column of source column x, or -1 (device); null = no decimation
     const int* sel_y;
-    const CUtensorMap* map; // host pointer to two TMA descriptors of src (boxes stream_box_width(r) x 8 and x 1), or null
+    const CUtensorMap* map; // host pointer to two TMA descriptors of src (boxes map_box x 8 and x 1), or null
+    int map_box;            // box width the descriptors were encoded with (each streaming kernel checks it is its own)
     int z0;      // first image of the batch this launch covers (the launch's blockIdx.z counts from here)
     int share;   // number of sibling launches expected to run concurrently (the grid is sized for 1/share of the GPU)
 };
@@ -90,7 +91,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // ---- launchers (each returns 0 or SIFT_GPU_E_CUDA; they count their launches in *launches) ----
 int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t* launches);
-int stream_box_width(int r);   // TMA box width the streaming kernel needs for radius r, or 0 if r has no streaming kernel
+int stream_box_width(int r, bool decimate);   // TMA box width the streaming kernel for (radius r, decimating or not) needs, or 0 if none
+int blur_prepare_device();     // per-device kernel attributes and occupancy figures; call after cudaSetDevice (sift_gpu_create does)
+// blur_slide.cu
+int launch_slide(const BlurArgs& a, int batch, bool fma, cudaStream_t s);   // -1: does not qualify
+int slide_box_width(int r);
+int slide_radius_for(int r);
+int slide_prepare_device();
 int stream_box_rows();         // rows of the multi-row TMA box (the other descriptor has 1-row boxes)
 int max_generic_radius();      // largest radius the generic tile kernel can hold in shared memory
 int launch_resize_nn(const float* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int dw,

@@ -225,6 +225,12 @@ static int strip_max_height() {
     static const int v = [] { const char* e = getenv("SIFT_GPU_STRIP_MAX_H"); return e ? atoi(e) : 300; }();
     return v;
 }
+// Levels between this height and strip_max_height() go to the streaming kernel when it has the radius (measured faster
+// from 270 rows up) and to the strip kernel otherwise.
+static int strip_preferred_height() {
+    static const int v = [] { const char* e = getenv("SIFT_GPU_STRIP_PREF_H"); return e ? atoi(e) : 200; }();
+    return v;
+}
 
 template <int SW>
 static int launch_strip_sw(const BlurArgs& a, int batch, bool fma, size_t smem, cudaStream_t s) {
@@ -232,12 +238,6 @@ static int launch_strip_sw(const BlurArgs& a, int batch, bool fma, size_t smem, 
     const int iw = strip_iw(SW, a.r), ntp = strip_ntp(a.r);
     int threads = (a.h * (SW / 4) + 31) / 32 * 32;
     threads = threads < 64 ? 64 : (threads > kStripMaxThreads ? kStripMaxThreads : threads);
-    static bool attr[2] = {false, false};
-    if (!attr[fma ? 1 : 0]) {
-        if (fma) SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        else SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr[fma ? 1 : 0] = true;
-    }
     if (fma) blur_strip_kernel<SW, true><<<grid, threads, smem, s>>>(a, iw, ntp);
     else blur_strip_kernel<SW, false><<<grid, threads, smem, s>>>(a, iw, ntp);
     SIFT_CUDA_TRY(cudaGetLastError());
@@ -245,8 +245,8 @@ static int launch_strip_sw(const BlurArgs& a, int batch, bool fma, size_t smem, 
 }
 
 // returns -1 when the level does not qualify
-static int launch_strip(const BlurArgs& a, int batch, bool fma, cudaStream_t s) {
-    if (a.h > strip_max_height() || a.r >= a.h || a.r >= a.w) return -1;
+static int launch_strip(const BlurArgs& a, int batch, bool fma, cudaStream_t s, int max_h) {
+    if (a.h > max_h || a.r >= a.h || a.r >= a.w) return -1;
     const size_t cap = 200 * 1024;
     int sw = 32;
     if (strip_smem_bytes(32, a.r, a.h) > cap || ((a.w + 31) / 32) * batch < 2 * 148) sw = 16;
@@ -577,6 +577,60 @@ __global__ void __launch_bounds__(64) blur_stream_kernel(const __grid_constant__
     }
 }
 
+// Per-device launch data of the streaming kernels (function attributes and occupancy are per device: a process may hold
+// contexts on several GPUs).  Filled by blur_prepare_device(), which sift_gpu_create calls after cudaSetDevice.
+struct StreamDevInfo { bool ready = false; int n_sm = 148; int cps[6][2][2] = {}; };   // [radius index][fma][decimate]
+static StreamDevInfo g_stream_dev[64];
+static int stream_radius_index(int r) { return r == 3 ? 0 : r == 5 ? 1 : r == 7 ? 2 : r == 10 ? 3 : r == 14 ? 4 : 5; }
+static const StreamDevInfo& stream_dev_info() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!g_stream_dev[dev].ready) blur_prepare_device();
+    return g_stream_dev[dev];
+}
+
+template <int R, bool FMA, bool DEC>
+static int stream_prepare_one(int* cps) {
+    using C = SC<R>;
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_stream_kernel<R, FMA, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    int n = 0;
+    SIFT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, FMA, DEC>, C::NWARP * 32, C::SMEM));
+    *cps = n > 0 ? n : 1;
+    return 0;
+}
+template <int R>
+static int stream_prepare_r(StreamDevInfo& d) {
+    const int i = stream_radius_index(R);
+    int rc;
+    if ((rc = stream_prepare_one<R, false, false>(&d.cps[i][0][0])) || (rc = stream_prepare_one<R, false, true>(&d.cps[i][0][1])) ||
+        (rc = stream_prepare_one<R, true, false>(&d.cps[i][1][0])) || (rc = stream_prepare_one<R, true, true>(&d.cps[i][1][1])))
+        return rc;
+    return 0;
+}
+
+int blur_prepare_device() {
+    int dev = 0;
+    SIFT_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    StreamDevInfo& d = g_stream_dev[dev];
+    if (d.ready) return 0;
+    if (cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.n_sm <= 0) d.n_sm = 148;
+    int rc;
+    if ((rc = stream_prepare_r<3>(d)) || (rc = stream_prepare_r<5>(d)) || (rc = stream_prepare_r<7>(d)) || (rc = stream_prepare_r<10>(d)) ||
+        (rc = stream_prepare_r<14>(d)) || (rc = stream_prepare_r<19>(d)))
+        return rc;
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_strip_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if ((rc = slide_prepare_device())) return rc;
+    d.ready = true;
+    return 0;
+}
+
 template <int R>
 static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t s) {
     using C = SC<R>;
@@ -585,33 +639,9 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
     // Rows per CTA.  More segments = more parallelism but RC + R extra rows to stage and row-filter per segment; fewer
     // segments = less overhead but a ragged last wave.  Pick the count with the best (last-wave fill) / (halo overhead).
     const int strips = (a.w + C::NWARP * C::WC - 1) / (C::NWARP * C::WC);
-    static int ctas_per_sm[2][2] = {{0, 0}, {0, 0}};
-    int& cps = ctas_per_sm[fma ? 1 : 0][a.sel_x ? 1 : 0];
-    if (cps == 0) {
-        int n = 0;
-        cudaError_t e;
-        // the occupancy query needs the opt-in shared-memory limit to be raised first
-        cudaFuncSetAttribute(blur_stream_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        cudaFuncSetAttribute(blur_stream_kernel<R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        cudaFuncSetAttribute(blur_stream_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        cudaFuncSetAttribute(blur_stream_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (fma) e = a.sel_x ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, true, true>, C::NWARP * 32, C::SMEM)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, true, false>, C::NWARP * 32, C::SMEM);
-        else e = a.sel_x ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, false, true>, C::NWARP * 32, C::SMEM)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_stream_kernel<R, false, false>, C::NWARP * 32, C::SMEM);
-        cps = (e == cudaSuccess && n > 0) ? n : 1;
-        (void)cudaGetLastError();
-    }
-    int n_sm = 148;
-    {
-        static int cached_sm = 0;
-        if (!cached_sm) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (cudaDeviceGetAttribute(&cached_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cached_sm <= 0) cached_sm = 148;
-        }
-        n_sm = cached_sm;
-    }
+    const StreamDevInfo& dv = stream_dev_info();
+    const int cps = dv.cps[stream_radius_index(R)][fma ? 1 : 0][a.sel_x ? 1 : 0];
+    const int n_sm = dv.n_sm;
     const double slots = (double)n_sm * cps / (a.share > 1 ? a.share : 1);
     int seg = a.h;
     double best = -1.0;
@@ -636,15 +666,7 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
         tp.po[m] = make_float2(tk(2 * m + 1), tk(2 * m + 2));
     }
     const bool dec = a.sel_x != nullptr;
-#define LAUNCH(F, D)                                                                                                        \
-    do {                                                                                                                    \
-        static bool attr = false;                                                                                           \
-        if (!attr) {                                                                                                        \
-            SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_stream_kernel<R, F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM)); \
-            attr = true;                                                                                                    \
-        }                                                                                                                   \
-        blur_stream_kernel<R, F, D><<<grid, C::NWARP * 32, C::SMEM, s>>>(a.map[0], a.map[1], sa, tp);                       \
-    } while (0)
+#define LAUNCH(F, D) blur_stream_kernel<R, F, D><<<grid, C::NWARP * 32, C::SMEM, s>>>(a.map[0], a.map[1], sa, tp)
     if (fma) { if (dec) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (dec) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
@@ -654,7 +676,20 @@ static int launch_stream_r(const BlurArgs& a, int batch, bool fma, cudaStream_t 
 
 int stream_box_rows() { return SC<5>::SR; }
 
-int stream_box_width(int r) {
+static int stream_old_box_width(int r) {
+    switch (r) {
+        case 3: return SC<3>::SWW;
+        case 5: return SC<5>::SWW;
+        case 7: return SC<7>::SWW;
+        case 10: return SC<10>::SWW;
+        case 14: return SC<14>::SWW;
+        case 19: return SC<19>::SWW;
+        default: return 0;
+    }
+}
+
+int stream_box_width(int r, bool decimate) {
+    if (!decimate && slide_box_width(r) > 0) return slide_box_width(r);
     switch (r) {
         case 3: return SC<3>::SWW;
         case 5: return SC<5>::SWW;
@@ -669,10 +704,18 @@ int stream_box_width(int r) {
 int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t* launches) {
     if (launches) ++*launches;
     {
-        const int rc = launch_strip(a, batch, fma, s);
+        const int rc = launch_strip(a, batch, fma, s, strip_preferred_height());
         if (rc >= 0) return rc;
     }
-    if (a.map && a.taps_host && a.w >= 32 && a.h >= 16) {
+    if (a.map && a.map_box == stream_box_width(a.r, a.sel_x != nullptr)) {
+        const int rc = launch_slide(a, batch, fma, s);
+        if (rc >= 0) return rc;
+    }
+    {
+        const int rc = launch_strip(a, batch, fma, s, strip_max_height());
+        if (rc >= 0) return rc;
+    }
+    if (a.map && a.taps_host && a.w >= 32 && a.h >= 16 && a.map_box == stream_old_box_width(a.r)) {
         switch (a.r) {
             case 3: return launch_stream_r<3>(a, batch, fma, s);
             case 5: return launch_stream_r<5>(a, batch, fma, s);
@@ -686,12 +729,7 @@ int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t
     const int r = a.r;
     const size_t smem = tile_smem_bytes(r);
     dim3 grid((a.w + kTW - 1) / kTW, (a.h + kTH - 1) / kTH, batch);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[fma ? 1 : 0]) {
-        if (fma) SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        else SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[fma ? 1 : 0] = true;
-    }
+    (void)stream_dev_info();   // makes sure this device's function attributes are set
     if (fma) blur_tile_kernel<true><<<grid, kBlurThreads, smem, s>>>(a);
     else blur_tile_kernel<false><<<grid, kBlurThreads, smem, s>>>(a);
     SIFT_CUDA_TRY(cudaGetLastError());

@@ -268,6 +268,7 @@ struct sift_gpu_ctx {
     float* d_taps = nullptr;
     std::vector<float> h_taps;
     int dead_blur_r[kMaxOctaves][kMaxGauss]{};
+    bool top_needed[kMaxOctaves]{};  // g(o, D) is somebody's nearest Gaussian (sift.cpp:205-218); otherwise nothing ever reads it and it is not stored
 
     // sizing
     int B = 1;
@@ -390,7 +391,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
     auto fail = [&](int code, const char* why) { if (p->status == SIFT_GPU_OK) { p->status = code; p->why = why; } };
     auto check_blur = [&](const BlurSpec& b, int w, int h) {
         if (w < b.r + 1 || h < b.r + 1) fail(SIFT_GPU_E_PRECONDITION, "separableConvolveX/Y(): kernel longer than line");
-        if (b.r > max_generic_radius() && !stream_box_width(b.r)) fail(SIFT_GPU_E_UNSUPPORTED, "blur radius exceeds the tile kernel's shared memory");
+        if (b.r > max_generic_radius() && !stream_box_width(b.r, false)) fail(SIFT_GPU_E_UNSUPPORTED, "blur radius exceeds the tile kernel's shared memory");
     };
     if (in_w < 1 || in_h < 1) fail(SIFT_GPU_E_INVALID, "empty image");
     if (c->prm.subpixel) {
@@ -449,6 +450,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
                 p->target_h.push_back(p->oh[to]);
             }
             p->class_target[(size_t)(e * D + i)] = slot;
+            if (ti == D) c->top_needed[to] = true;
         }
     for (int si = 0; si < c->n_slots; ++si) {
         Slot& S = c->slots[si];
@@ -480,8 +482,8 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
             cudaMemcpy(ps.targets_dev, ps.targets_host.data(), sizeof(LevelRef) * ps.targets_host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
             fail(SIFT_GPU_E_CUDA, "plan upload failed");
         // TMA descriptors (box width depends on the blur radius); a missing descriptor only means the generic kernel runs
-        auto mk = [&](CUtensorMap* m, const float* base, int w, int h, int pitch, size_t stride, int r) {
-            const int bw = stream_box_width(r);
+        auto mk = [&](CUtensorMap* m, const float* base, int w, int h, int pitch, size_t stride, int r, bool decimate = false) {
+            const int bw = stream_box_width(r, decimate);
             return bw > 0 && tma::make_image_map(&m[0], base, w, h, c->B, (size_t)pitch, stride, bw, stream_box_rows()) &&
                    tma::make_image_map(&m[1], base, w, h, c->B, (size_t)pitch, stride, bw, 1);
         };
@@ -495,7 +497,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
             for (int j = 1; j <= D; ++j)
                 ps.has_chain[o][j] = mk(ps.map_chain[o][j], S.d_gauss[o][j - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->chain_blur[o][j].r);
             if (o < O - 1)
-                ps.has_reduce[o] = mk(ps.map_reduce[o], S.d_gauss[o][D - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->reduce_blur[o].r);
+                ps.has_reduce[o] = mk(ps.map_reduce[o], S.d_gauss[o][D - 1], p->ow[o], p->oh[o], p->pitch[o], c->maxP[o], c->reduce_blur[o].r, true);
         }
     }
     return p;
@@ -617,7 +619,13 @@ static BlurArgs blur_args(const sift_gpu_ctx* c, const BlurSpec& b, const float*
     a.src_pitch = spitch; a.dst_pitch = dpitch; a.dog_pitch = gpitch;
     a.w = w; a.h = h; a.taps = c->d_taps + b.tap_off; a.taps_host = c->h_taps.data() + b.tap_off; a.r = b.r;
     a.map = map;
+    a.map_box = 0;   // set by the caller that knows which box the descriptors were encoded with
     return a;
+}
+
+static bool keep_top_levels() {
+    static const bool v = getenv("SIFT_GPU_KEEP_TOP_LEVELS") != nullptr;
+    return v;
 }
 
 // Sift::calculate's upsample (sift.cpp:20-21) + _createDOGs (sift.cpp:381-417) for the images [z0, z0 + cnt) of the pass.
@@ -641,6 +649,7 @@ static int run_pyramid_group(sift_gpu_ctx* c, Slot& S, const Plan* p, const Plan
     auto launch = [&](BlurArgs a) {
         a.z0 = z0;
         a.share = share;
+        a.map_box = a.map ? stream_box_width(a.r, a.sel_x != nullptr) : 0;
         mark(a.sel_x ? "reduce" : (a.dog ? "blur+dog" : "blur"), a.r, a.w, a.h);
         return launch_blur(a, cnt, c->fma, s, L);
     };
@@ -659,10 +668,14 @@ static int run_pyramid_group(sift_gpu_ctx* c, Slot& S, const Plan* p, const Plan
     CTX_TRY(launch(blur_args(c, c->base_blur, base_src, base_stride, base_pitch, S.d_gauss[0][0], c->maxP[0], p->pitch[0], nullptr, 0, 0,
                              p->ow[0], p->oh[0], ps.has_base ? ps.map_base : nullptr)));
     for (int o = 0; o < O; ++o) {
-        for (int j = 1; j <= D; ++j)
-            CTX_TRY(launch(blur_args(c, c->chain_blur[o][j], S.d_gauss[o][j - 1], c->maxP[o], p->pitch[o], S.d_gauss[o][j], c->maxP[o],
+        for (int j = 1; j <= D; ++j) {
+            // the top Gaussian of an octave is only stored when a keypoint class takes it as its nearest Gaussian (octaves >= 5 with the
+            // default schedule); its DoG is all the pipeline needs otherwise (sift_gpu_debug_get_level recomputes it on demand)
+            float* g_out = (j == D && !c->top_needed[o] && !keep_top_levels()) ? nullptr : S.d_gauss[o][j];
+            CTX_TRY(launch(blur_args(c, c->chain_blur[o][j], S.d_gauss[o][j - 1], c->maxP[o], p->pitch[o], g_out, c->maxP[o],
                                      p->pitch[o], S.d_dog[o][j - 1], c->maxP[o], p->pitch[o], p->ow[o], p->oh[o],
                                      ps.has_chain[o][j] ? ps.map_chain[o][j] : nullptr)));
+        }
         if (o < O - 1) {
             // alg::reduceToNextLevel: blur with the level's own label sigma, keep only the pixels the resize picks
             BlurArgs a = blur_args(c, c->reduce_blur[o], S.d_gauss[o][D - 1], c->maxP[o], p->pitch[o], S.d_gauss[o + 1][0], c->maxP[o + 1],
@@ -1201,6 +1214,7 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
         return set_error(nullptr, SIFT_GPU_E_UNSUPPORTED, "too many octaves / DoGs per octave");
     if (params->max_width < 1 || params->max_height < 1 || params->max_batch < 1)
         return set_error(nullptr, SIFT_GPU_E_INVALID, "max_width/max_height/max_batch must be positive");
+    if (params->max_batch > 4096) return set_error(nullptr, SIFT_GPU_E_UNSUPPORTED, "max_batch above 4096 (the batch is a grid dimension)");
     if ((params->subpixel ? 2 : 1) * (long)params->max_width > 65535 || (params->subpixel ? 2 : 1) * (long)params->max_height > 32767)
         return set_error(nullptr, SIFT_GPU_E_UNSUPPORTED, "image too large for u16 keypoint coordinates");
     int ndev = 0;
@@ -1217,6 +1231,7 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
     int rc = 0;
     auto body = [&]() -> int {
         CTX_CUDA(cudaSetDevice(params->device));
+        CTX_TRY(blur_prepare_device());   // function attributes / occupancy figures are per device
         CTX_TRY(build_schedule(c));
         CTX_TRY(alloc_buffers(c));
         return 0;
@@ -1416,6 +1431,16 @@ int sift_gpu_debug_get_level(sift_gpu_ctx* c, int image_idx, int octave, int ele
         return set_error(c, SIFT_GPU_E_INVALID, "level index out of range");
     CTX_CUDA(cudaSetDevice(c->prm.device));
     const float* src = (kind == SIFT_GPU_KIND_DOG ? S.d_dog[octave][elem] : S.d_gauss[octave][elem]) + (size_t)image_idx * c->maxP[octave];
+    if (out && kind == SIFT_GPU_KIND_GAUSS && elem == c->D && !c->top_needed[octave] && !keep_top_levels()) {
+        // the pass did not store this level (nothing reads it): blur g(o, D-1) of this one image now
+        BlurArgs a = blur_args(c, c->chain_blur[octave][elem], S.d_gauss[octave][elem - 1] + (size_t)image_idx * c->maxP[octave], 0, p->pitch[octave],
+                               S.d_gauss[octave][elem] + (size_t)image_idx * c->maxP[octave], 0, p->pitch[octave], nullptr, 0, 0, p->ow[octave],
+                               p->oh[octave], nullptr);
+        a.z0 = 0;
+        a.share = 1;
+        CTX_TRY(launch_blur(a, 1, c->fma, S.stream, nullptr));
+        CTX_CUDA(cudaStreamSynchronize(S.stream));
+    }
     if (width) *width = p->ow[octave];
     if (height) *height = p->oh[octave];
     if (scale) *scale = kind == SIFT_GPU_KIND_DOG ? c->d_scale[octave][elem] : c->g_scale[octave][elem];
@@ -1436,7 +1461,7 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
     int r = 0;
     std::vector<float> taps = gaussian_taps(sigma, &r);
     if (w < r + 1 || h < r + 1) return set_error(c, SIFT_GPU_E_PRECONDITION, "separableConvolveX/Y(): kernel longer than line");
-    if (r > max_generic_radius() && !stream_box_width(r)) return set_error(c, SIFT_GPU_E_UNSUPPORTED, "radius too large");
+    if (r > max_generic_radius() && !stream_box_width(r, false)) return set_error(c, SIFT_GPU_E_UNSUPPORTED, "radius too large");
     int dw = w, dh = h;
     if (mode == 1) { dw = (w + 1) / 2; dh = (h + 1) / 2; }
     if (mode == 2) { dw = 2 * w; dh = 2 * h; }
@@ -1455,13 +1480,14 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
         cu(cudaMemcpy(d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice));
     }
     CUtensorMap map[2];
-    const int bw = stream_box_width(r);
+    const int bw = stream_box_width(r, mode == 1);
     const bool has_map = !rc && bw > 0 && tma::make_image_map(&map[0], d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw, stream_box_rows()) &&
                          tma::make_image_map(&map[1], d_src, w, h, 1, (size_t)sp, level_px(sp, h), bw, 1);
     if (!rc) {
         BlurArgs a{};
         a.src = d_src; a.src_pitch = sp; a.w = w; a.h = h; a.taps = d_taps; a.taps_host = taps.data(); a.r = r;
         a.map = has_map ? map : nullptr;
+        a.map_box = has_map ? bw : 0;
         if (mode == 1) {
             // reduceToNextLevel: decimation fused into the blur epilogue
             std::vector<int> mx = resize_index_map(w, dw), my = resize_index_map(h, dh), inv((size_t)(w + h), -1);
