@@ -18,7 +18,10 @@
 #include <iostream>
 #include <set>
 #include <vector>
+#include <cstdlib>
 #include <cstring>
+#include <new>
+#include <type_traits>
 #include <exception>
 #include <memory>
 #include <string>
@@ -115,6 +118,7 @@ class MultiArray : public MultiArrayView<N, T> {
     MultiArray() : leaked_(false) {}
     explicit MultiArray(const Shape2& shape) : leaked_(false) { allocate(shape, true); }
     MultiArray(MultiArrayIndex w, MultiArrayIndex h) : leaked_(false) { allocate(Shape2(w, h), true); }
+
     MultiArray(const MultiArray& rhs) : view_type(), leaked_(false) { take(rhs); }
     // Vigra's converting constructor is implicit: views passed where `const MultiArray&` is expected are deep-copied.
     MultiArray(const view_type& rhs) : leaked_(false) { deep_from(rhs); }
@@ -171,7 +175,12 @@ class MultiArray : public MultiArrayView<N, T> {
    private:
     void allocate(const Shape2& shape, bool zero) {
         const std::size_t n = (std::size_t)(shape[0] * shape[1]);
-        buf_ = std::shared_ptr<T>(zero ? new T[n]() : new T[n], std::default_delete<T[]>());
+        // calloc: large zero-initialised arrays come as fresh zero pages that cost nothing until touched (the two temporaries
+        // of alg::convolveWithGauss are never touched when REF_SHIM_FAST's memoised blur answers)
+        static_assert(std::is_trivial<T>::value, "calloc'd storage");
+        T* raw = static_cast<T*>(zero ? std::calloc(n ? n : 1, sizeof(T)) : std::malloc((n ? n : 1) * sizeof(T)));
+        if (!raw) throw std::bad_alloc();
+        buf_ = std::shared_ptr<T>(raw, [](T* q) { std::free(q); });
         this->m_shape = shape;
         this->m_stride = Shape2(1, shape[0]);
         this->m_ptr = buf_.get();

@@ -5,10 +5,10 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-enum Op { FFMA, FMUL, FADD, FFMA2, FMUL2, FADD2, FFMA2_U, FMUL2_U, MULADD2, MULADD2_U, FFMA_U, MIX_M2_A1 };
+enum Op { FFMA, FMUL, FADD, FFMA2, FMUL2, FADD2, FFMA2_U, FMUL2_U, MULADD2, MULADD2_U, FFMA_U, MIX_M2_A1, FFMA2_BR, FFMA2_BU, FFMA2_SHIFT };
 static const char* names[] = {"FFMA r,r,r", "FMUL r,r", "FADD r,r", "FFMA2 r,r,r", "FMUL2 r,r", "FADD2 r,r", "FFMA2 r,U,r", "FMUL2 r,U",
-                              "FMUL2+FFMA2(one) r", "FMUL2(U)+FFMA2(one)", "FFMA r,U,r", "FMUL2(U)+2xFADD"};
-static const int results_per_iter[] = {1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 1, 2};  // useful tap-results per accumulator per iteration
+                              "FMUL2+FFMA2(one) r", "FMUL2(U)+FFMA2(one)", "FFMA r,U,r", "FMUL2(U)+2xFADD", "FFMA2 r,bcast(r),r", "FFMA2 r,bcast(U),r", "FFMA2 shift d!=c"};
+static const int results_per_iter[] = {1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 1, 2, 2, 2, 2};  // useful tap-results per accumulator per iteration
 
 struct P { float2 t[8]; float2 one; };
 
@@ -53,6 +53,9 @@ __global__ void __launch_bounds__(1024) probe(const P p, float* out, long long* 
                 if (OP == FADD2) acc[i] = add2(acc[i], v[i]);
                 if (OP == MULADD2) acc[i] = fma2(mul2(v[i], tr), p.one, acc[i]);
                 if (OP == MULADD2_U) acc[i] = fma2(mul2(v[i], p.t[k]), p.one, acc[i]);
+                if (OP == FFMA2_BR) acc[i] = fma2(v[i], make_float2(tr.x, tr.x), acc[i]);
+                if (OP == FFMA2_BU) acc[i] = fma2(v[i], make_float2(p.t[k].x, p.t[k].x), acc[i]);
+                if (OP == FFMA2_SHIFT) acc[i] = fma2(v[0], make_float2(tr.x, tr.x), acc[(i + 1) % NA]);
                 if (OP == MIX_M2_A1) { float2 m = mul2(v[i], p.t[k]); acc[i].x = __fadd_rn(__fadd_rn(acc[i].x, m.x), m.y); }
             }
         }
@@ -103,7 +106,7 @@ int main() {
     printf("SMs %d\n", sms);
     run<FFMA>(sms, out, cyc, p); run<FFMA_U>(sms, out, cyc, p); run<FMUL>(sms, out, cyc, p); run<FADD>(sms, out, cyc, p);
     run<FFMA2>(sms, out, cyc, p); run<FFMA2_U>(sms, out, cyc, p); run<FMUL2>(sms, out, cyc, p); run<FMUL2_U>(sms, out, cyc, p); run<FADD2>(sms, out, cyc, p);
-    run<MULADD2>(sms, out, cyc, p); run<MULADD2_U>(sms, out, cyc, p); run<MIX_M2_A1>(sms, out, cyc, p);
+    run<FFMA2_BR>(sms, out, cyc, p); run<FFMA2_BU>(sms, out, cyc, p); run<FFMA2_SHIFT>(sms, out, cyc, p); run<MULADD2>(sms, out, cyc, p); run<MULADD2_U>(sms, out, cyc, p); run<MIX_M2_A1>(sms, out, cyc, p);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
