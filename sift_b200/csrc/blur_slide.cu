@@ -347,6 +347,153 @@ __global__ void __launch_bounds__(64) blur_slide_kernel(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Decimating variant: alg::reduceToNextLevel (reference algorithms.cpp:24-36) = blur with the level's own sigma, then the
+// nearest-neighbour resize, which picks source column sx(k) = 2k + p and source row sy(m) = 2m + q with p, q in {0, 1}
+// constant over long runs (Vigra's accumulated index walk: even sizes switch from 2i to 2i+1 once, at the middle).
+// Only the picked pixels are computed along x: a warp owns 64 DESTINATION columns of one parity run; its row pass filters
+// the 64 picked source columns of every source row (window of 8 + 2*RPAD staged floats per 4 outputs), the column pass runs
+// over those 64 columns exactly like the plain kernel, and a step's result is stored only when its source row is picked.
+// Half the row-pass and half the column-pass arithmetic of a full blur, a quarter of the stores.
+struct DecRegion { int k_begin, k_end, parity, first_block; };   // destination columns [k_begin, k_end): source x = 2k + parity
+struct SlideDecArgs {
+    BlurArgs a;
+    int seg, ahead, n_regions;
+    DecRegion reg[4];
+};
+
+template <int R>
+struct SLD {
+    using B = SL<R, false>;
+    static constexpr int SWW = (128 + 2 * B::RPAD + 31) / 32 * 32;   // staged source floats per row (128-B multiple)
+    static constexpr int NW = 8 + 2 * B::RPAD;                       // row-pass window of 4 picked outputs
+    static constexpr int STAGE_FLOATS = B::CH * SWW;
+    static constexpr int warp_floats(int nstg) { return nstg * STAGE_FLOATS + B::MID_FLOATS; }
+    static constexpr size_t smem(int nstg) { return sizeof(float) * (size_t)(B::NWARP * warp_floats(nstg)) + B::NWARP * (B::MAX_AHEAD + 1) * sizeof(uint64_t); }
+    static_assert(SWW <= 256 && (STAGE_FLOATS * 4) % 128 == 0 && (B::MID_FLOATS * 4) % 128 == 0, "TMA box / alignment");
+};
+
+template <int R, bool FMA, int P, int NWV>
+__device__ __forceinline__ float4 sl_dec_outputs(const float (&wv)[NWV], const SlideTaps<R>& tp) {
+    using B = SL<R, false>;
+    float4 o;
+    o.x = sl_row_output<R, FMA, B::OFF + P + 0>(wv, tp);
+    o.y = sl_row_output<R, FMA, B::OFF + P + 2>(wv, tp);
+    o.z = sl_row_output<R, FMA, B::OFF + P + 4>(wv, tp);
+    o.w = sl_row_output<R, FMA, B::OFF + P + 6>(wv, tp);
+    return o;
+}
+
+template <int R, bool FMA>
+__global__ void __launch_bounds__(64) blur_slide_dec_kernel(const __grid_constant__ CUtensorMap map8, const __grid_constant__ CUtensorMap map1,
+                                                            const SlideDecArgs sa, const SlideTaps<R> taps) {
+    using B = SL<R, false>;
+    using C = SLD<R>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nstg = sa.ahead + 1;
+    const int warp_floats = nstg * C::STAGE_FLOATS + B::MID_FLOATS;
+    float* stage = reinterpret_cast<float*>(smem_raw) + warp * warp_floats;
+    float* mid = stage + nstg * C::STAGE_FLOATS;
+    const uint32_t stage_u = tma::smem_u32(stage);
+    const uint32_t full_u = tma::smem_u32(reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + B::NWARP * warp_floats) + warp * (B::MAX_AHEAD + 1));
+
+    const BlurArgs& a = sa.a;
+    const int b = blockIdx.z + a.z0;
+    const int w = a.w, h = a.h;
+    int ri = 0;
+    while (ri + 1 < sa.n_regions && (int)blockIdx.x >= sa.reg[ri + 1].first_block) ++ri;
+    const DecRegion rg = sa.reg[ri];
+    // first destination column of this warp; runs start at an even column (the TMA box must start on a 16-byte boundary:
+    // x = 2*k0 - RPAD a multiple of 4), columns below k_begin are computed with the wrong parity and never stored
+    const int k0 = (rg.k_begin & ~1) + (((int)blockIdx.x - rg.first_block) * B::NWARP + warp) * B::WC;
+    if (k0 >= rg.k_end) return;
+    const int xs = 2 * k0;                                  // staged column c holds source x = xs - RPAD + c
+    const int y0 = blockIdx.y * sa.seg;
+    const int y1 = min(y0 + sa.seg, h);
+    const int n_virtual = (y1 - y0) + 2 * R;
+    const int n_chunks = (n_virtual + B::CH - 1) / B::CH;
+    const int v_first = y0 - R;
+    const bool edge = (xs - B::RPAD < 0) || (xs - B::RPAD + C::SWW > w);
+
+    if (lane == 0) {
+        tma::prefetch_map(&map8);
+        for (int s = 0; s < nstg; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_u + 8 * s) : "memory");
+        tma::fence_barrier_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < nstg && i < n_chunks; ++i)
+            sl_issue_chunk(stage_u + i * C::STAGE_FLOATS * 4, full_u + 8 * i, &map8, &map1, xs - B::RPAD, v_first + i * B::CH, h, b, C::SWW);
+    }
+    float tk[R + 1];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) tk[j] = taps.tk[j];
+    const float one = taps.one;
+
+    const int cg = lane & 15, rsub = lane >> 4;
+    const int k = k0 + 2 * lane;                            // this lane's destination columns k, k + 1
+    const bool ok0 = k >= rg.k_begin && k < rg.k_end, ok1 = k + 1 >= rg.k_begin && k + 1 < rg.k_end;
+    float* const dst_img = a.dst + (size_t)b * a.dst_stride + k;
+
+    float2 acc[B::NACC];
+#pragma unroll
+    for (int q = 0; q < B::NACC; ++q) acc[q] = make_float2(0.0f, 0.0f);
+
+    int s = 0;
+    uint32_t parity = 0;
+    const float* const mid_lane = mid + 2 * lane;
+#pragma unroll 1
+    for (int i = 0; i < n_chunks; ++i) {
+        float* const st = stage + s * C::STAGE_FLOATS;
+        sl_wait(full_u + 8 * s, parity);
+        if (edge) sl_patch_columns(st, B::CH, w, xs, B::RPAD, R, C::SWW, lane);
+        {
+            float wv[2][C::NW];
+            auto load_window = [&](float (&dstw)[C::NW], int rw) {
+                const float* srow = st + rw * C::SWW + 8 * cg;
+#pragma unroll
+                for (int q = 0; q < C::NW / 4; ++q) {
+                    const float4 f = *reinterpret_cast<const float4*>(srow + 4 * q);
+                    dstw[4 * q] = f.x; dstw[4 * q + 1] = f.y; dstw[4 * q + 2] = f.z; dstw[4 * q + 3] = f.w;
+                }
+            };
+            load_window(wv[0], rsub);
+#pragma unroll
+            for (int q = 0; q < B::CH / 2; ++q) {
+                const int rw = rsub + 2 * q;
+                if (q + 1 < B::CH / 2) load_window(wv[(q + 1) & 1], rw + 2);
+                const float (&wq)[C::NW] = wv[q & 1];
+                const float4 o4 = rg.parity ? sl_dec_outputs<R, FMA, 1>(wq, taps) : sl_dec_outputs<R, FMA, 0>(wq, taps);
+                *reinterpret_cast<float4*>(mid + rw * B::MW + 4 * cg) = o4;
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && i + nstg < n_chunks)
+            sl_issue_chunk(stage_u + s * C::STAGE_FLOATS * 4, full_u + 8 * s, &map8, &map1, xs - B::RPAD, v_first + (i + nstg) * B::CH, h, b, C::SWW);
+
+        // column pass: step r consumes virtual row i*8 + r and completes source row yo = y0 - 2R + i*8 + r
+        const int t0 = i * B::CH;
+#pragma unroll
+        for (int r = 0; r < B::CH; ++r) {
+            const float2 hv = *reinterpret_cast<const float2*>(mid_lane + r * B::MW);
+            const float2 res = sl_col_step<R, FMA>(acc, hv, tk, one);
+            const int t = t0 + r;
+            const int yo = y0 - 2 * R + t;
+            if (t >= 2 * R && t < n_virtual) {               // warp-uniform
+                const int drow = __ldg(a.sel_y + yo);        // destination row of this source row, or -1
+                if (drow >= 0) {
+                    float* o = dst_img + (size_t)drow * a.dst_pitch;
+                    if (ok0) o[0] = res.x;
+                    if (ok1) o[1] = res.y;
+                }
+            }
+        }
+        __syncwarp();
+        if (++s == nstg) { s = 0; parity ^= 1u; }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 static constexpr int kSlideRadii[] = {3, 5, 7, 10, 14, 19, 27};
 
@@ -400,6 +547,7 @@ static int slide_prepare_r(SlideDevInfo& d, int idx) {
     return 0;
 }
 
+static int slide_dec_prepare_device(int dev);
 // Per-device set-up (function attributes are per device): called from sift_gpu_create after cudaSetDevice.
 int slide_prepare_device() {
     int dev = 0;
@@ -412,6 +560,7 @@ int slide_prepare_device() {
     if ((rc = slide_prepare_r<3>(d, 0)) || (rc = slide_prepare_r<5>(d, 1)) || (rc = slide_prepare_r<7>(d, 2)) || (rc = slide_prepare_r<10>(d, 3)) ||
         (rc = slide_prepare_r<14>(d, 4)) || (rc = slide_prepare_r<19>(d, 5)) || (rc = slide_prepare_r<27>(d, 6)))
         return rc;
+    if ((rc = slide_dec_prepare_device(dev))) return rc;
     d.ready = true;
     return 0;
 }
@@ -485,6 +634,133 @@ int launch_slide(const BlurArgs& a, int batch, bool fma, cudaStream_t s) {
         case 14: return launch_slide_r<14>(a, batch, fma, 4, s);
         case 19: return launch_slide_r<19>(a, batch, fma, 5, s);
         case 27: return launch_slide_r<27>(a, batch, fma, 6, s);
+        default: return -1;
+    }
+}
+
+
+int slide_dec_box_width(int r) {
+    switch (slide_radius_for(r)) {
+        case 3: return SLD<3>::SWW;
+        case 5: return SLD<5>::SWW;
+        case 7: return SLD<7>::SWW;
+        case 10: return SLD<10>::SWW;
+        case 14: return SLD<14>::SWW;
+        case 19: return SLD<19>::SWW;
+        default: return 0;   // 27: the window would not fit the register budget; those launches take another kernel
+    }
+}
+
+static int g_dec_cps[64][8][2];
+template <int R>
+static int slide_dec_prepare_r(int dev, int idx) {
+    const size_t smem = SLD<R>::smem(slide_ahead() + 1);
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_slide_dec_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SIFT_CUDA_TRY(cudaFuncSetAttribute(blur_slide_dec_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    SIFT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_slide_dec_kernel<R, false>, 64, smem));
+    g_dec_cps[dev][idx][0] = n > 0 ? n : 1;
+    SIFT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blur_slide_dec_kernel<R, true>, 64, smem));
+    g_dec_cps[dev][idx][1] = n > 0 ? n : 1;
+    return 0;
+}
+static int slide_dec_prepare_device(int dev) {
+    int rc;
+    if ((rc = slide_dec_prepare_r<3>(dev, 0)) || (rc = slide_dec_prepare_r<5>(dev, 1)) || (rc = slide_dec_prepare_r<7>(dev, 2)) ||
+        (rc = slide_dec_prepare_r<10>(dev, 3)) || (rc = slide_dec_prepare_r<14>(dev, 4)) || (rc = slide_dec_prepare_r<19>(dev, 5)))
+        return rc;
+    return 0;
+}
+
+template <int R>
+static int launch_slide_dec_r(const BlurArgs& a, int batch, bool fma, int idx, cudaStream_t s) {
+    using B = SL<R, false>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!g_slide_dev[dev].ready) {
+        const int rc = slide_prepare_device();
+        if (rc) return rc;
+    }
+    const SlideDevInfo& d = g_slide_dev[dev];
+    // runs of constant parity in the column pick; every picked source column must be 2k or 2k + 1
+    SlideDecArgs sa;
+    sa.a = a;
+    sa.n_regions = 0;
+    int k = 0, blocks = 0;
+    for (int x = 0; x < a.w; ++x) {
+        const int dk = a.sel_x_host[x];
+        if (dk < 0) continue;
+        if (dk != k || (x - 2 * k != 0 && x - 2 * k != 1)) return -1;
+        const int par = x - 2 * k;
+        if (sa.n_regions == 0 || sa.reg[sa.n_regions - 1].parity != par) {
+            if (sa.n_regions) {
+                DecRegion& pr = sa.reg[sa.n_regions - 1];
+                pr.k_end = k;
+                blocks += (pr.k_end - (pr.k_begin & ~1) + B::NWARP * B::WC - 1) / (B::NWARP * B::WC);
+            }
+            if (sa.n_regions == 4) return -1;
+            sa.reg[sa.n_regions++] = DecRegion{k, k, par, blocks};
+        }
+        ++k;
+    }
+    if (sa.n_regions == 0) return -1;
+    {
+        DecRegion& pr = sa.reg[sa.n_regions - 1];
+        pr.k_end = k;
+        blocks += (pr.k_end - (pr.k_begin & ~1) + B::NWARP * B::WC - 1) / (B::NWARP * B::WC);
+    }
+    for (int y = 0; y < a.h; ++y) {   // rows may be picked in any pattern; only sanity-check the range
+        const int dy = a.sel_y_host[y];
+        if (dy < -1) return -1;
+    }
+    const int r = a.r, pad = R - r;
+    float tkv[2 * R + 1];
+    for (int j = 0; j <= 2 * R; ++j) tkv[j] = (j >= pad && j <= pad + 2 * r) ? a.taps_host[2 * r - (j - pad)] : 0.0f;
+    for (int j = 0; j < R; ++j)
+        if (tkv[j] != tkv[2 * R - j]) return -1;
+    SlideTaps<R> tp;
+    tp.one = 1.0f;
+    for (int j = 0; j <= R; ++j) tp.tk[j] = tkv[j];
+    for (int m = 0; m < R; ++m) {
+        tp.pe[m] = make_float2(tkv[2 * m], tkv[2 * m + 1]);
+        tp.po[m] = make_float2(tkv[2 * m + 1], tkv[2 * m + 2]);
+    }
+    const int cps = g_dec_cps[dev][idx][fma ? 1 : 0];
+    static const bool use_share = [] { const char* e = getenv("SIFT_GPU_SLIDE_SHARE"); return e ? atoi(e) != 0 : true; }();
+    const double slots = (double)d.n_sm * cps / (use_share && a.share > 1 ? a.share : 1);
+    int seg = a.h;
+    double best = -1.0;
+    for (int nseg = 1; nseg <= (a.h + 15) / 16; ++nseg) {
+        const int sg = ((a.h + nseg - 1) / nseg + B::CH - 1) / B::CH * B::CH;
+        const int real_segs = (a.h + sg - 1) / sg;
+        const double tiles = (double)blocks * real_segs * batch;
+        const double waves = std::ceil(tiles / slots);
+        const double fill = tiles / (waves * slots);
+        const double overhead = (double)(sg + 2 * R + B::CH) / sg;
+        const double score = fill / overhead;
+        if (score > best + 1e-9) { best = score; seg = sg; }
+    }
+    sa.seg = seg;
+    sa.ahead = slide_ahead();
+    dim3 grid(blocks, (a.h + seg - 1) / seg, batch);
+    if (fma) blur_slide_dec_kernel<R, true><<<grid, 64, SLD<R>::smem(sa.ahead + 1), s>>>(a.map[0], a.map[1], sa, tp);
+    else blur_slide_dec_kernel<R, false><<<grid, 64, SLD<R>::smem(sa.ahead + 1), s>>>(a.map[0], a.map[1], sa, tp);
+    SIFT_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// returns -1 when the launch does not qualify
+int launch_slide_dec(const BlurArgs& a, int batch, bool fma, cudaStream_t s) {
+    static const bool off = getenv("SIFT_GPU_NO_SLIDE_DEC") != nullptr || getenv("SIFT_GPU_NO_SLIDE") != nullptr;
+    if (off || !a.sel_x || !a.sel_x_host || !a.sel_y_host || !a.map || !a.taps_host || !a.dst || a.dog || a.w < 64 || a.h < 16) return -1;
+    switch (slide_radius_for(a.r)) {
+        case 3: return launch_slide_dec_r<3>(a, batch, fma, 0, s);
+        case 5: return launch_slide_dec_r<5>(a, batch, fma, 1, s);
+        case 7: return launch_slide_dec_r<7>(a, batch, fma, 2, s);
+        case 10: return launch_slide_dec_r<10>(a, batch, fma, 3, s);
+        case 14: return launch_slide_dec_r<14>(a, batch, fma, 4, s);
+        case 19: return launch_slide_dec_r<19>(a, batch, fma, 5, s);
         default: return -1;
     }
 }

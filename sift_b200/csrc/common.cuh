@@ -75,6 +75,8 @@ struct BlurArgs {
     int r;
     const int* sel_x; // decimation: destination column of source column x, or -1 (device); null = no decimation
     const int* sel_y;
+    const int* sel_x_host; // the same maps in host memory (the decimating streaming kernel derives its launch geometry from them), or null
+    const int* sel_y_host;
     const CUtensorMap* map; // host pointer to two TMA descriptors of src (boxes map_box x 8 and x 1), or null
     int map_box;            // box width the descriptors were encoded with (each streaming kernel checks it is its own)
     int z0;      // first image of the batch this launch covers (the launch's blockIdx.z counts from here)
@@ -95,6 +97,8 @@ int stream_box_width(int r, bool decimate);   // TMA box width the streaming ker
 int blur_prepare_device();     // per-device kernel attributes and occupancy figures; call after cudaSetDevice (sift_gpu_create does)
 // blur_slide.cu
 int launch_slide(const BlurArgs& a, int batch, bool fma, cudaStream_t s);   // -1: does not qualify
+int launch_slide_dec(const BlurArgs& a, int batch, bool fma, cudaStream_t s);   // decimating launches; -1: does not qualify
+int slide_dec_box_width(int r);
 int slide_box_width(int r);
 int slide_radius_for(int r);
 int slide_prepare_device();

@@ -690,6 +690,7 @@ static int stream_old_box_width(int r) {
 
 int stream_box_width(int r, bool decimate) {
     if (!decimate && slide_box_width(r) > 0) return slide_box_width(r);
+    if (decimate && slide_dec_box_width(r) > 0) return slide_dec_box_width(r);
     switch (r) {
         case 3: return SC<3>::SWW;
         case 5: return SC<5>::SWW;
@@ -708,7 +709,7 @@ int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t
         if (rc >= 0) return rc;
     }
     if (a.map && a.map_box == stream_box_width(a.r, a.sel_x != nullptr)) {
-        const int rc = launch_slide(a, batch, fma, s);
+        const int rc = a.sel_x ? launch_slide_dec(a, batch, fma, s) : launch_slide(a, batch, fma, s);
         if (rc >= 0) return rc;
     }
     {

@@ -172,6 +172,7 @@ struct Plan {
     int status = SIFT_GPU_OK;
     std::string why;
     int* d_maps = nullptr;  // all index maps, one allocation
+    std::vector<int> h_maps; // host copy (launch geometry of the decimating kernel)
     size_t up_mx = 0, up_my = 0;
     size_t sel_x[kMaxOctaves] = {0}, sel_y[kMaxOctaves] = {0};  // decimation: inverse index maps (offsets into d_maps)
     int total_cols = 0;
@@ -426,6 +427,7 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
     };
     if (c->prm.subpixel) { p->up_mx = push_map(in_w, in_w * 2); p->up_my = push_map(in_h, in_h * 2); }
     for (int o = 0; o + 1 < O; ++o) { p->sel_x[o] = push_inverse(p->ow[o], p->ow[o + 1]); p->sel_y[o] = push_inverse(p->oh[o], p->oh[o + 1]); }
+    p->h_maps = maps;
     if (!maps.empty()) {
         if (cudaMalloc(&p->d_maps, sizeof(int) * maps.size()) != cudaSuccess ||
             cudaMemcpy(p->d_maps, maps.data(), sizeof(int) * maps.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -682,6 +684,8 @@ static int run_pyramid_group(sift_gpu_ctx* c, Slot& S, const Plan* p, const Plan
                                    p->pitch[o + 1], nullptr, 0, 0, p->ow[o], p->oh[o], ps.has_reduce[o] ? ps.map_reduce[o] : nullptr);
             a.sel_x = p->d_maps + p->sel_x[o];
             a.sel_y = p->d_maps + p->sel_y[o];
+            a.sel_x_host = p->h_maps.data() + p->sel_x[o];
+            a.sel_y_host = p->h_maps.data() + p->sel_y[o];
             CTX_TRY(launch(a));
         }
     }
@@ -1496,6 +1500,7 @@ static int debug_blur_impl(sift_gpu_ctx* c, const float* src, int w, int h, floa
             cu(cudaMalloc(&d_map, sizeof(int) * inv.size()));
             if (!rc) cu(cudaMemcpy(d_map, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice));
             a.dst = d_out; a.dst_pitch = dp; a.sel_x = d_map; a.sel_y = d_map + w;
+            a.sel_x_host = inv.data(); a.sel_y_host = inv.data() + w;
             if (!rc) rc = launch_blur(a, 1, c->fma, c->slots[0].stream, nullptr);
         } else {
             a.dst = mode == 0 ? d_out : d_blur; a.dst_pitch = sp;

@@ -192,7 +192,7 @@ def test_blur_precondition_maps_to_exception(ctx):
         ctx.blur(np.zeros((5, 40), np.float32), 1.6)
 
 
-@pytest.mark.parametrize("w,h", [(64, 48), (61, 75), (135, 270), (4, 3), (3, 5)])
+@pytest.mark.parametrize("w,h", [(64, 48), (61, 75), (135, 270), (4, 3), (3, 5), (488, 512), (333, 251), (511, 203), (64, 201), (130, 509), (244, 300)])
 def test_reduce_and_increase(ctx, w, h):
     img = synth_frame(max(w, 8), max(h, 8), w * h)[:h, :w].copy()
     sigma = 0.3 if min(w, h) < 6 else 1.6
