@@ -3,8 +3,10 @@
 //   inverse(-H) fails -> reject; linearSolve(inv, grad) fails -> reject; any component > 127.5 ->
 //   reject; f = dot(grad, ext) * (0.5 + D(x,y)) [double], f < 7.65 -> reject; det < 0 -> reject;
 //   tr^2/det > 12.1f -> reject.  loc/scale are never moved.
-// One thread per candidate; unfiltered candidates are appended (warp-aggregated atomic) to the
-// survivor list together with their canonical position, which the host order replay needs.
+// One thread per candidate writes the verdict into the candidate list; a second kernel (one CTA per image, block-wide
+// prefix sums) then compacts the unfiltered candidates IN CANONICAL ORDER into the survivor list, each with its
+// position in the candidate vector (the host's std::sort replay works on those positions, and no longer has to sort
+// an atomically appended list back into order).
 #include "common.cuh"
 #include "vigra_qr.cuh"
 
@@ -77,33 +79,81 @@ __global__ void __launch_bounds__(128) eliminate_kernel(const ScanLayer* __restr
             keep = !filtered;
             cl[i].filtered = filtered ? 1 : 0;
         }
-        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-        if (ballot) {
-            const int lane = threadIdx.x & 31;
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(&n_surv[b], (uint32_t)__popc(ballot));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-            if (keep) {
-                const uint32_t slot = slot0 + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
-                if (slot < surv_stride) {
-                    Surv s;
-                    s.canon = i;
-                    s.x = c.x; s.y = c.y; s.octave = c.octave; s.index = c.index; s.pad = 0;
-                    survivors[(size_t)b * surv_stride + slot] = s;
-                }
+        (void)keep;
+    }
+}
+
+// Ordered compaction of the unfiltered candidates of image blockIdx.x.
+__global__ void __launch_bounds__(1024) compact_survivors_kernel(const Cand* __restrict__ cands, size_t cand_stride, const uint32_t* __restrict__ n_cand,
+                                                                 Surv* __restrict__ survivors, size_t surv_stride, uint32_t* __restrict__ n_surv) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const int b = blockIdx.x;
+    const uint32_t n = n_cand[b];
+    const Cand* cl = cands + (size_t)b * cand_stride;
+    Surv* out = survivors + (size_t)b * surv_stride;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    constexpr int PER = 4;   // consecutive candidates per thread and round
+    for (uint32_t base = 0; base < n; base += 1024 * PER) {
+        const uint32_t i0 = base + (uint32_t)threadIdx.x * PER;
+        Cand c[PER];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            if (i0 + q < n) {
+                c[q] = cl[i0 + q];
+                cnt += c[q].filtered ? 0u : 1u;
+            } else {
+                c[q].filtered = 1;
             }
         }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            warp_sums[lane] = ws;  // inclusive
+        }
+        __syncthreads();
+        uint32_t slot = carry + (wid ? warp_sums[wid - 1] : 0u) + incl - cnt;
+#pragma unroll
+        for (int q = 0; q < PER; ++q)
+            if (!c[q].filtered) {
+                if (slot < surv_stride) {
+                    Surv sv;
+                    sv.canon = i0 + q;
+                    sv.x = c[q].x; sv.y = c[q].y; sv.octave = c[q].octave; sv.index = c[q].index; sv.pad = 0;
+                    out[slot] = sv;
+                }
+                ++slot;
+            }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = slot;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) n_surv[b] = carry;
 }
 
 int launch_eliminate(const ScanLayer* layers_dev, int n_layers, Cand* cands, size_t cand_stride,
                      const uint32_t* n_cand, Surv* survivors, size_t surv_stride, uint32_t* n_surv, int dogs_per_epoch,
                      int batch, cudaStream_t s, uint64_t* launches) {
-    SIFT_CUDA_TRY(cudaMemsetAsync(n_surv, 0, sizeof(uint32_t) * (size_t)batch, s));
     dim3 grid(148 * 4, batch);
     eliminate_kernel<<<grid, 128, 0, s>>>(layers_dev, n_layers, cands, cand_stride, n_cand, survivors, surv_stride, n_surv,
                                          dogs_per_epoch);
-    if (launches) ++*launches;
+    compact_survivors_kernel<<<batch, 1024, 0, s>>>(cands, cand_stride, n_cand, survivors, surv_stride, n_surv);
+    if (launches) *launches += 2;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -768,25 +768,8 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
         t = n;
     };
     auto t_ph = tick();
-    // the device appends survivors in arbitrary order: back to canonical order with an LSD radix sort on `canon` (< n_cand)
-    std::vector<Surv> S(surv_in, surv_in + n_surv);
-    {
-        std::vector<Surv> tmp(n_surv);
-        int bits = 1;
-        while (bits < 32 && (n_cand >> bits) != 0) ++bits;
-        const int passes = (bits + 10) / 11;
-        Surv* src = S.data();
-        Surv* dst = tmp.data();
-        for (int ps = 0; ps < passes; ++ps) {
-            uint32_t count[2049] = {0};
-            const int sh = 11 * ps;
-            for (uint32_t i = 0; i < n_surv; ++i) ++count[((src[i].canon >> sh) & 2047u) + 1];
-            for (int i = 0; i < 2048; ++i) count[i + 1] += count[i];
-            for (uint32_t i = 0; i < n_surv; ++i) dst[count[(src[i].canon >> sh) & 2047u]++] = src[i];
-            std::swap(src, dst);
-        }
-        if (src != S.data()) S.swap(tmp);
-    }
+    // the device compacts survivors in canonical order (compact_survivors_kernel): `canon` ascends
+    const Surv* S = surv_in;
     lap(0, t_ph);
     // first cleanup over all candidates
     std::vector<uint32_t> L1;  // survivor slots in vector order
