@@ -167,6 +167,60 @@ def cpu_baseline_sample(seconds_budget=20.0):
     return {"value": n / t, "unit": "images/s", "cores": 1, "kind": kind, "sample": f"{n} synthetic 1080p frames, 1 thread; {what}"}
 
 
+def measure_configs(device, flags, literal_cpu=True):
+    """BASELINE.json configs 1, 2 and 4 (config 3/5 are the main line): one image per call on one GPU — latency from a host frame to
+    keypoints + descriptors in host memory, the pyramid stage's time and its share of the HBM roofline — and, for the sizes the
+    reference's CPU path can finish (north_star: parrot, 600x600; 1500x1500 takes 9-11 minutes and is run with --literal-1500),
+    the LITERAL reference (oracle/_ref/libref.so: every copy deep, no memoised blur) on one host thread, next to the
+    README's own numbers (reference README.md:68-71: ~300x300 0.7 s, ~600x600 15 s, ~1500x1500 11 min)."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from sift_b200 import capi
+    from sift_b200.synth import synth_frame
+
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    k = capi.SQRT2_F32
+    parrot = np.load(os.path.join(ROOT, "tests", "golden", "parrot_r.npy")).astype(np.float32)
+    cases = [("config1_parrot_488x600", parrot, 4, False),
+             ("config2_600x600_subpixel", synth_frame(600, 600, 0), 4, True),
+             ("config4_3840x2160_subpixel_6oct", synth_frame(3840, 2160, 0), 6, True)]
+    out = {}
+    for name, img, octaves, sub in cases:
+        h, w = img.shape
+        g = capi.SiftGpu(DPE, octaves, 1.6, k, sub, max_width=w, max_height=h, max_batch=1, device=device, flags=flags | capi.FLAG_SERIAL)
+        lat, pyr, n = [], [], 0
+        for i in range(7):
+            t0 = time.perf_counter()
+            r = g.run([img], raise_on_error=False)[0]
+            lat.append(1e3 * (time.perf_counter() - t0))
+            pyr.append(g.timings()["pyramid_ms"])
+            n = int(r["kps"].size)
+        g.close()
+        lat, pyr = sorted(lat[2:]), sorted(pyr[2:])
+        pb = pyramid_bytes(w, h, octaves, DPE, sub)
+        out[name] = {"gpu_latency_ms": lat[len(lat) // 2], "pyramid_ms": pyr[len(pyr) // 2], "pyramid_algorithmic_bytes": pb,
+                     "pyramid_gbs": pb / (pyr[len(pyr) // 2] * 1e-3) / 1e9, "pyramid_frac_of_hbm_peak": pb / (pyr[len(pyr) // 2] * 1e-3) / 1e9 / peak,
+                     "keypoints": n, "octaves": octaves, "subpixel": sub}
+    if literal_cpu and ol.ref_available(fast=False):
+        L = ol.ref_lib(fast=False)
+        for name, img, octaves, readme in (("literal_cpu_300x300", synth_frame(300, 300, 0), 4, "~0.7 s"),
+                                            ("literal_cpu_parrot_488x600", parrot, 4, None),
+                                            ("literal_cpu_600x600", synth_frame(600, 600, 0), 4, "~15 s")):
+            o = ol.Oracle(DPE, octaves, 1.6, float(np.float32(np.sqrt(2.0))), False, L=L)
+            dt, nk = o.time_calculate(img)
+            out[name] = {"seconds": dt, "keypoints": nk, "threads": 1, "readme_says": readme,
+                         "what": "reference sift.cpp + algorithms.cpp compiled unmodified (deep copies, no memoisation), CLI defaults"}
+        out["literal_cpu_1500x1500"] = {"seconds": None, "readme_says": "~11 min",
+                                        "note": "526 s measured in the build container (BASELINE.md); bench.py --literal-1500 repeats it"}
+    return out
+
+
 def bind_to_gpu_cpus(index):
     """Multi-GPU host: keep this rank's threads and its pinned buffers on the CPUs (NUMA node) next to its GPU, so the frame
     uploads do not cross the socket interconnect.  Best effort; returns the number of CPUs bound to, or None."""
@@ -287,17 +341,25 @@ def run_ours(args):
     torch.cuda.synchronize()
     n_roof = max(1, min(args.steps, 4))
     acc_r = do_steps(dev_frames.data_ptr(), capi.MEM_DEVICE, n_roof, 1)
+    # the same stage in the other blur arithmetic (exact <-> fused multiply-add), measured the same way, for the record
+    other_flags = args.flags ^ capi.FLAG_FMA_BLUR
+    g.close()
+    g = capi.SiftGpu(DPE, OCTAVES, 1.6, capi.SQRT2_F32, False, max_width=W, max_height=H, max_batch=args.device_batch,
+                     device=local_rank, flags=other_flags | capi.FLAG_SERIAL)
+    do_steps(dev_frames.data_ptr(), capi.MEM_DEVICE, 1, 0)
+    torch.cuda.synchronize()
+    acc_o = do_steps(dev_frames.data_ptr(), capi.MEM_DEVICE, n_roof, 1)
 
     # run() is synchronous (it returns after its last stream sync), so the host clock around the K steps equals the
     # device-side span; span_ms (CUDA events on the library's stream) is reported beside it.  Max over ranks.
-    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_r["pyramid_ms"], wall_u8],
+    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_r["pyramid_ms"], wall_u8, acc_o["pyramid_ms"]],
                                     [args.steps * B, acc_d["launches"], acc_d["kps"], acc_d["cands"]])
     if rank != 0:
         g.close()
         dist.barrier()
         dist.destroy_process_group()
         return
-    wall_d, wall_h, span_d, pyr_ms, wall_u8 = mx
+    wall_d, wall_h, span_d, pyr_ms, wall_u8, pyr_other_ms = mx
     images, launches, kps, cands = sm
     value = images / wall_d
     e2e = images / wall_h
@@ -340,15 +402,21 @@ def run_ours(args):
                      "algorithmic_bytes_per_image": pyr_bytes, "pyramid_ms_per_image": pyr_ms / (n_roof * B),
                      "measured": "serial context (SIFT_GPU_FLAG_SERIAL), %d steps, CUDA events around the stage" % n_roof, "traffic": traffic,
                      "serial_stage_ms_per_image": {k2: v / (n_roof * B) for k2, v in acc_r["stages"].items()}},
+        "roofline_other_blur": {"blur": "exact mul+add" if other_flags & capi.FLAG_FMA_BLUR == 0 else "fma (SIFT_GPU_FLAG_FMA_BLUR: DoG within 1e-6 relative, same keypoint set to 99.9 %, "
+                                        "descriptors comparable only under a pinned order; tests/test_gpu_fma_mode.py)",
+                                "achieved": pyr_bytes * n_roof * B / (pyr_other_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": pyr_bytes * n_roof * B / (pyr_other_ms * 1e-3) / 1e9 / peak, "pyramid_ms_per_image": pyr_other_ms / (n_roof * B)},
         "device_span_ms_per_step": span_d / args.steps,
         "timing": "host clock around K synchronous library calls, bracketed by cuda synchronize + barrier, max over ranks; device_span_ms_per_step is the CUDA-event span (first to last stream event of each call) of the same steps",
         "stage_ms_per_image": {k2: v / (args.steps * B) for k2, v in acc_d["stages"].items()},
     }
+    g.close()
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()
     else:
         line["cpu_baseline"] = None
-    g.close()
+    if world == 1 and not args.no_configs:
+        line["configs"] = measure_configs(local_rank, args.flags, literal_cpu=not args.no_cpu_baseline)
     print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()
@@ -366,9 +434,22 @@ def main():
     ap.add_argument("--device-batch", type=int, default=64, help="frames per device pass (ctx max_batch); several passes are in flight")
     ap.add_argument("--flags", type=int, default=0, help="SIFT_GPU_FLAG_* bits (1 canonical order, 4 FMA blur)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the single-image measurements of BASELINE configs 1, 2, 4")
+    ap.add_argument("--literal-1500", action="store_true", help="only time the literal reference CPU path on a 1500x1500 frame (minutes)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.literal_1500:
+        import numpy as np
+
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        from sift_b200.synth import synth_frame
+
+        o = ol.Oracle(DPE, 4, 1.6, float(np.float32(np.sqrt(2.0))), False, L=ol.ref_lib(fast=False))
+        dt, nk = o.time_calculate(synth_frame(1500, 1500, 0))
+        print(json.dumps({"literal_cpu_1500x1500": {"seconds": dt, "keypoints": nk, "threads": 1, "readme_says": "~11 min"}}))
+        return
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
