@@ -20,7 +20,9 @@
 // multiply feeding a packed add into one FFMA2 even under -fmad=false; see pyramid.cu) -> bit-identical to the
 // reference's mulss/addss; FMA mode = one FFMA2 per tap pair.  Radii are instantiated for a few R; a blur of radius
 // r runs on the smallest R >= r with zero taps added symmetrically (acc + 0*v == acc for the finite values of an image).
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -59,6 +61,15 @@ struct SL {
                   "TMA destinations must stay 128-B aligned");
 };
 
+// Resident CTAs per SM the kernels are compiled for (__launch_bounds__): what shared memory allows with two stages, capped where
+// the register budget that goes with it (65536 / 64 / n) would spill the 2R accumulators and the row-pass windows.
+template <int R, bool FMA, int MODE>
+constexpr int slide_min_blocks() {
+    const int by_smem = (int)((227 * 1024) / (SL<R, MODE != 0>::smem(2) + 1024));
+    const int cap = R <= 10 ? 12 : (R <= 14 ? 7 : (R <= 19 ? (FMA ? 5 : 4) : 3));
+    return by_smem < cap ? by_smem : cap;
+}
+
 template <int R>
 struct SlideTaps {        // tk[j] = tap applied to source index x - R + j; symmetric (tk[j] == tk[2R - j], checked on the host)
     float tk[R + 1];      // j <= R; the column pass uses them as (tk, tk): ptxas folds that into a scalar-broadcast FFMA2 operand
@@ -67,10 +78,25 @@ struct SlideTaps {        // tk[j] = tap applied to source index x - R + j; symm
     float2 po[R];         // (tk[2m+1], tk[2m+2])
 };
 
+// Work partition of a launch: the rows of all images of the launch form one linear space g = image * h + y, cut into equal
+// contiguous shares, one per "row lane"; a row lane is `strips` warps with consecutive global warp numbers, one per
+// 64-column strip, which therefore walk down the same rows side by side (whole rows stream from DRAM, and the horizontal
+// halo a strip shares with its neighbours is in L2 when the neighbour asks for it).  The grid is what the GPU holds at once
+// (SMs x resident CTAs): a grid of independent CTAs a little smaller than the resident slots gets spread unevenly by the
+// hardware (4 to 7 CTAs per SM measured).  A share that crosses an image boundary is cut into two pieces; every piece costs
+// one vertical halo (2R rows).
+// (Measured and dropped: dynamic row ranges with work stealing between the warps of a strip.  The warp schedulers favour the
+// warps launched first, so equal shares finish between 150 and 280 us in a 296 us launch, but the launch is bound by what
+// the SM sustains with all warps resident, not by that tail: stealing evened the finish times out and left the span where it
+// was, at the price of registers.)
 struct SlideArgs {
     BlurArgs a;
-    int seg;              // output rows per CTA
+    int strips;           // 64-column warp strips per image
+    int lanes;            // row lanes: warps gw >= lanes * strips have nothing to do
+    uint32_t share;       // rows of the linear space per row lane
+    uint32_t total;       // images * h
     int ahead;            // chunks in flight per warp (stages = ahead + 1)
+    unsigned long long* probe;   // development (SIFT_GPU_SLIDE_PROBE): per warp {start ns, end ns, smid, hardware warp id}, or null
 };
 
 // one output of the row pass: sum over j of tk[j] * wv[BASE + j], ascending j
@@ -114,16 +140,36 @@ __device__ __forceinline__ float sl_row_output(const float (&wv)[NWV], const Sli
     }
 }
 
-// Reflect patch of one staged chunk (edge strips only): staged column c holds x = xs - rpad + c; TMA zero-filled what lies
-// outside the image; columns -1..-r and w..w+r-1 get their mirrored pixels, which are staged in the same row.
-__device__ __noinline__ void sl_patch_columns(float* st, int rows, int w, int xs, int rpad, int r, int sww, int lane) {
-    const int n = 2 * r;
-    for (int e = lane; e < rows * n; e += 32) {
-        const int rr = e / n, k = e - rr * n;
-        const int gx = k < r ? -1 - k : w + (k - r);
-        const int c = gx - (xs - rpad);
-        const int cs = sl_reflect(gx, w) - (xs - rpad);
-        if (c >= 0 && c < sww && cs >= 0 && cs < sww) st[rr * sww + c] = st[rr * sww + cs];
+// Reflect patch of a staged chunk (edge strips only): staged column c holds x = x_first + c; TMA zero-filled what lies outside
+// the image; columns -1..-r and w..w+r-1 get their mirrored pixels, which are staged in the same row.  A strip's columns are
+// fixed, so lane k < r works out once which staged column it patches on the left (x = -1-k) and on the right (x = w+k) and
+// where its source sits; per chunk that leaves eight loads and stores per side.  (The first version recomputed the indices
+// with a division per element: an edge warp then took 1.6x as long per chunk as an interior one, and the whole launch
+// waited for the two edge strips.)
+struct SlPatch { uint32_t left, right; };   // staged columns (destination | source << 16) on the left and on the right, or ~0
+__device__ __forceinline__ SlPatch sl_patch_setup(int lane, int w, int x_first, int r, int sww) {
+    SlPatch p{~0u, ~0u};
+    if (lane < r) {
+        int gx = -1 - lane, c = gx - x_first, cs = sl_reflect(gx, w) - x_first;
+        if (c >= 0 && c < sww && cs >= 0 && cs < sww) p.left = (uint32_t)c | ((uint32_t)cs << 16);
+        gx = w + lane; c = gx - x_first; cs = sl_reflect(gx, w) - x_first;
+        if (c >= 0 && c < sww && cs >= 0 && cs < sww) p.right = (uint32_t)c | ((uint32_t)cs << 16);
+    }
+    return p;
+}
+template <int ROWS>
+__device__ __forceinline__ void sl_patch_apply(float* st, const SlPatch& p, int sww) {
+    if (p.left != ~0u) {
+        float* d = st + (p.left & 0xffffu);
+        const float* q = st + (p.left >> 16);
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) d[rr * sww] = q[rr * sww];
+    }
+    if (p.right != ~0u) {
+        float* d = st + (p.right & 0xffffu);
+        const float* q = st + (p.right >> 16);
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) d[rr * sww] = q[rr * sww];
     }
     tma::fence_proxy_async();  // generic-proxy writes above vs. the next TMA write into this stage
     __syncwarp();
@@ -235,27 +281,13 @@ __global__ void __launch_bounds__(64) blur_slide_kernel(const __grid_constant__ 
     const uint32_t full_u = tma::smem_u32(reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + C::NWARP * warp_floats) + warp * (C::MAX_AHEAD + 1));
 
     const BlurArgs& a = sa.a;
-    const int b = blockIdx.z + a.z0;
     const int w = a.w, h = a.h;
-    const int xs = (blockIdx.x * C::NWARP + warp) * C::WC;
-    if (xs >= w) return;                                    // warps are independent: no barrier below
-    const int y0 = blockIdx.y * sa.seg;
-    const int y1 = min(y0 + sa.seg, h);
-    const int n_virtual = (y1 - y0) + 2 * R;                // virtual rows y0 - R .. y1 + R - 1 feed this segment
-    const int n_chunks = (n_virtual + C::CH - 1) / C::CH;
-    const int v_first = y0 - R;
-    const bool edge = (xs - C::RPAD < 0) || (xs - C::RPAD + C::SWW > w);
-
     if (lane == 0) {
         tma::prefetch_map(&map8);
         for (int s = 0; s < nstg; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_u + 8 * s) : "memory");
         tma::fence_barrier_init();
     }
     __syncwarp();
-    if (lane == 0) {
-        for (int i = 0; i < nstg && i < n_chunks; ++i)
-            sl_issue_chunk(stage_u + i * C::STAGE_FLOATS * 4, full_u + 8 * i, &map8, &map1, xs - C::RPAD, v_first + i * C::CH, h, b, C::SWW);
-    }
 
     float tk[R + 1];
 #pragma unroll
@@ -264,86 +296,130 @@ __global__ void __launch_bounds__(64) blur_slide_kernel(const __grid_constant__ 
 
     // row pass: lane = (row parity, column group)
     const int cg = lane & 15, rsub = lane >> 4;
+    const float* const mid_lane = mid + 2 * lane;
+    const int opitch = MODE == 2 ? a.dog_pitch : a.dst_pitch;
+    const size_t pitch_bytes = (size_t)opitch * sizeof(float);
+
+    // this warp's strip and its row lane's share of the linear (image, row) space
+    const uint32_t gw = blockIdx.x * C::NWARP + warp;
+    const uint32_t row_lane = gw / (uint32_t)sa.strips;
+    if (row_lane >= (uint32_t)sa.lanes) return;              // warps are independent: no CTA-wide barrier anywhere
+    const int xs = (int)(gw - row_lane * (uint32_t)sa.strips) * C::WC;
+    const SlPatch patch = sl_patch_setup(lane, w, xs - C::RPAD, R, C::SWW);
+    const bool edge = __any_sync(0xffffffffu, (patch.left & patch.right) != ~0u);
+    unsigned long long t_start = 0;
+    if (sa.probe) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    uint32_t g = row_lane * sa.share;
+    const uint32_t g_end = min(sa.total, g + sa.share);
+    int s = 0;                 // stage of the next chunk, its mbarrier phase parity: the stages are used round-robin across pieces
+    uint32_t parity = 0;
+    int cur = 0;               // block of `cen` the current chunk's centre pixels go to
+    // state of the current piece (one loop over all chunks of all pieces: a nested loop costs ptxas ~40 registers)
+    int i = 0, n_chunks = 0, n_virtual = 0, v_first = 0, bz = 0;
     // column pass: columns xs + 2*lane, +1 (for an odd width the second column lies in the row's padding: pitch % 32 == 0)
     const int x = xs + 2 * lane;
     const bool active = x < w;
-    // address of output row (t - 2R) of the segment at the lane's columns: it starts 2R rows above the segment and moves down one
-    // row per step; stores only happen once t >= 2R.  MODE 0/1: dst (dog = dst + dog_delta), MODE 2: dog.
-    const float* obase = MODE == 2 ? a.dog + (size_t)b * a.dog_stride : a.dst + (size_t)b * a.dst_stride;
-    const int opitch = MODE == 2 ? a.dog_pitch : a.dst_pitch;
-    const size_t pitch_bytes = (size_t)opitch * sizeof(float);
-    char* row = reinterpret_cast<char*>(const_cast<float*>(obase)) + ((ptrdiff_t)(y0 - 2 * R) * opitch + (active ? x : 0)) * (ptrdiff_t)sizeof(float);
-    const ptrdiff_t dog_delta =
-        MODE == 1 ? (reinterpret_cast<const char*>(a.dog + (size_t)b * a.dog_stride) - reinterpret_cast<const char*>(a.dst + (size_t)b * a.dst_stride)) : 0;
-
+    char* row = nullptr;
+    ptrdiff_t dog_delta = 0;
     float2 acc[C::NACC];
-#pragma unroll
-    for (int k = 0; k < C::NACC; ++k) acc[k] = make_float2(0.0f, 0.0f);
-
-    int s = 0;                 // stage of chunk i, its mbarrier phase parity
-    uint32_t parity = 0;
-    int cur = 0;               // block of `cen` the current chunk's centre pixels go to
-    const float* const mid_lane = mid + 2 * lane;
 #pragma unroll 1
-    for (int i = 0; i < n_chunks; ++i) {
-        float* const st = stage + s * C::STAGE_FLOATS;
-        sl_wait(full_u + 8 * s, parity);
-        if (edge) sl_patch_columns(st, C::CH, w, xs, C::RPAD, R, C::SWW, lane);
-
-        // blocks of `cen`: cb[q] = the block q chunks back (cb[0] = this chunk's)
-        const float* cb[C::NB + 1];
-#pragma unroll
-        for (int q = 0; q < C::NB; ++q) {
-            int blk = cur - q;
-            blk = blk < 0 ? blk + C::NB : blk;
-            cb[q] = cen + blk * (C::CH * C::MW) + 2 * lane;
-        }
-        cb[C::NB] = nullptr;
-
-        // ---- row pass: lane = 4 adjacent columns x rows rsub, rsub+2, rsub+4, rsub+6 (a quarter-warp reads 128 contiguous bytes).
-        // The window of the next row is loaded before the current one is filtered (two register sets), so the shared-memory
-        // latency of one row hides behind the arithmetic of the other.
-        {
-            float wv[2][C::NW];
-            auto load_window = [&](float (&dstw)[C::NW], int rw) {
-                const float* srow = st + rw * C::SWW + 4 * cg;
-#pragma unroll
-                for (int k = 0; k < C::NW / 4; ++k) {
-                    const float4 f = *reinterpret_cast<const float4*>(srow + 4 * k);
-                    dstw[4 * k] = f.x; dstw[4 * k + 1] = f.y; dstw[4 * k + 2] = f.z; dstw[4 * k + 3] = f.w;
+    for (;;) {
+        if (i == n_chunks) {   // next piece
+            if (g >= g_end) break;
+            const uint32_t b = g / (uint32_t)h;
+            const int y0 = (int)(g - b * (uint32_t)h);
+            const int y1 = min(h, y0 + (int)(g_end - g));
+            g += (uint32_t)(y1 - y0);
+            bz = (int)b + a.z0;
+            n_virtual = (y1 - y0) + 2 * R;                // virtual rows y0 - R .. y1 + R - 1 feed this piece
+            n_chunks = (n_virtual + C::CH - 1) / C::CH;
+            v_first = y0 - R;
+            i = 0;
+            if (lane == 0) {
+                int st = s;
+                for (int q = 0; q < nstg && q < n_chunks; ++q) {
+                    sl_issue_chunk(stage_u + st * C::STAGE_FLOATS * 4, full_u + 8 * st, &map8, &map1, xs - C::RPAD, v_first + q * C::CH, h, bz, C::SWW);
+                    if (++st == nstg) st = 0;
                 }
-            };
-            load_window(wv[0], rsub);
-#pragma unroll
-            for (int q = 0; q < C::CH / 2; ++q) {
-                const int rw = rsub + 2 * q;
-                if (q + 1 < C::CH / 2) load_window(wv[(q + 1) & 1], rw + 2);
-                const float (&wq)[C::NW] = wv[q & 1];
-                if (DOG)   // the four centre pixels are window elements RPAD .. RPAD+3
-                    *reinterpret_cast<float4*>(cen + cur * (C::CH * C::MW) + rw * C::MW + 4 * cg) =
-                        make_float4(wq[C::RPAD], wq[C::RPAD + 1], wq[C::RPAD + 2], wq[C::RPAD + 3]);
-                float4 o4;
-                o4.x = sl_row_output<R, FMA, C::OFF + 0>(wq, taps);
-                o4.y = sl_row_output<R, FMA, C::OFF + 1>(wq, taps);
-                o4.z = sl_row_output<R, FMA, C::OFF + 2>(wq, taps);
-                o4.w = sl_row_output<R, FMA, C::OFF + 3>(wq, taps);
-                *reinterpret_cast<float4*>(mid + rw * C::MW + 4 * cg) = o4;
             }
+            // address of output row (t - 2R) of the piece at the lane's columns: it starts 2R rows above the piece and moves down one
+            // row per step; stores only happen once t >= 2R.  MODE 0/1: dst (dog = dst + dog_delta), MODE 2: dog.
+            const float* obase = MODE == 2 ? a.dog + (size_t)bz * a.dog_stride : a.dst + (size_t)bz * a.dst_stride;
+            row = reinterpret_cast<char*>(const_cast<float*>(obase)) + ((ptrdiff_t)(y0 - 2 * R) * opitch + (active ? x : 0)) * (ptrdiff_t)sizeof(float);
+            dog_delta = MODE == 1 ? (reinterpret_cast<const char*>(a.dog + (size_t)bz * a.dog_stride) - reinterpret_cast<const char*>(a.dst + (size_t)bz * a.dst_stride)) : 0;
+#pragma unroll
+            for (int k = 0; k < C::NACC; ++k) acc[k] = make_float2(0.0f, 0.0f);
         }
-        __syncwarp();   // mid / cen rows visible to the whole warp; every lane is done with stage s
-        // the row pass was the stage's only reader (the DoG's centre pixels went to `cen`): refill it with chunk i + nstg right away
-        if (lane == 0 && i + nstg < n_chunks)
-            sl_issue_chunk(stage_u + s * C::STAGE_FLOATS * 4, full_u + 8 * s, &map8, &map1, xs - C::RPAD, v_first + (i + nstg) * C::CH, h, b, C::SWW);
+        {
+            float* const st = stage + s * C::STAGE_FLOATS;
+            sl_wait(full_u + 8 * s, parity);
+            if (edge) sl_patch_apply<C::CH>(st, patch, C::SWW);
 
-        // ---- column pass: 8 steps ----
-        const int t0 = i * C::CH;
-        if (t0 >= 2 * R && t0 + C::CH <= n_virtual)
-            sl_col_chunk<R, FMA, MODE, false>(acc, mid_lane, cb, tk, one, row, pitch_bytes, dog_delta, active, t0, n_virtual);
-        else
-            sl_col_chunk<R, FMA, MODE, true>(acc, mid_lane, cb, tk, one, row, pitch_bytes, dog_delta, active, t0, n_virtual);
-        __syncwarp();   // every lane is done with mid
-        if (DOG) cur = cur + 1 == C::NB ? 0 : cur + 1;
-        if (++s == nstg) { s = 0; parity ^= 1u; }
+            // blocks of `cen`: cb[q] = the block q chunks back (cb[0] = this chunk's)
+            const float* cb[C::NB + 1];
+#pragma unroll
+            for (int q = 0; q < C::NB; ++q) {
+                int blk = cur - q;
+                blk = blk < 0 ? blk + C::NB : blk;
+                cb[q] = cen + blk * (C::CH * C::MW) + 2 * lane;
+            }
+            cb[C::NB] = nullptr;
+
+            // ---- row pass: lane = 4 adjacent columns x rows rsub, rsub+2, rsub+4, rsub+6 (a quarter-warp reads 128 contiguous bytes).
+            // The window of the next row is loaded before the current one is filtered (two register sets), so the shared-memory
+            // latency of one row hides behind the arithmetic of the other.
+            {
+                float wv[2][C::NW];
+                auto load_window = [&](float (&dstw)[C::NW], int rw) {
+                    const float* srow = st + rw * C::SWW + 4 * cg;
+#pragma unroll
+                    for (int k = 0; k < C::NW / 4; ++k) {
+                        const float4 f = *reinterpret_cast<const float4*>(srow + 4 * k);
+                        dstw[4 * k] = f.x; dstw[4 * k + 1] = f.y; dstw[4 * k + 2] = f.z; dstw[4 * k + 3] = f.w;
+                    }
+                };
+                load_window(wv[0], rsub);
+#pragma unroll
+                for (int q = 0; q < C::CH / 2; ++q) {
+                    const int rw = rsub + 2 * q;
+                    if (q + 1 < C::CH / 2) load_window(wv[(q + 1) & 1], rw + 2);
+                    const float (&wq)[C::NW] = wv[q & 1];
+                    if (DOG)   // the four centre pixels are window elements RPAD .. RPAD+3
+                        *reinterpret_cast<float4*>(cen + cur * (C::CH * C::MW) + rw * C::MW + 4 * cg) =
+                            make_float4(wq[C::RPAD], wq[C::RPAD + 1], wq[C::RPAD + 2], wq[C::RPAD + 3]);
+                    float4 o4;
+                    o4.x = sl_row_output<R, FMA, C::OFF + 0>(wq, taps);
+                    o4.y = sl_row_output<R, FMA, C::OFF + 1>(wq, taps);
+                    o4.z = sl_row_output<R, FMA, C::OFF + 2>(wq, taps);
+                    o4.w = sl_row_output<R, FMA, C::OFF + 3>(wq, taps);
+                    *reinterpret_cast<float4*>(mid + rw * C::MW + 4 * cg) = o4;
+                }
+            }
+            __syncwarp();   // mid / cen rows visible to the whole warp; every lane is done with stage s
+            // the row pass was the stage's only reader (the DoG's centre pixels went to `cen`): refill it with chunk i + nstg right away
+            if (lane == 0 && i + nstg < n_chunks)
+                sl_issue_chunk(stage_u + s * C::STAGE_FLOATS * 4, full_u + 8 * s, &map8, &map1, xs - C::RPAD, v_first + (i + nstg) * C::CH, h, bz, C::SWW);
+
+            // ---- column pass: 8 steps ----
+            const int t0 = i * C::CH;
+            if (t0 >= 2 * R && t0 + C::CH <= n_virtual)
+                sl_col_chunk<R, FMA, MODE, false>(acc, mid_lane, cb, tk, one, row, pitch_bytes, dog_delta, active, t0, n_virtual);
+            else
+                sl_col_chunk<R, FMA, MODE, true>(acc, mid_lane, cb, tk, one, row, pitch_bytes, dog_delta, active, t0, n_virtual);
+            __syncwarp();   // every lane is done with mid
+            if (DOG) cur = cur + 1 == C::NB ? 0 : cur + 1;
+            if (++s == nstg) { s = 0; parity ^= 1u; }
+            ++i;
+        }
+    }
+    if (sa.probe && lane == 0) {
+        unsigned long long t_end;
+        unsigned smid, wid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        unsigned long long* o = sa.probe + 4ull * gw;
+        o[0] = t_start; o[1] = t_end; o[2] = smid; o[3] = wid;
     }
 }
 
@@ -355,10 +431,13 @@ __global__ void __launch_bounds__(64) blur_slide_kernel(const __grid_constant__ 
 // the 64 picked source columns of every source row (window of 8 + 2*RPAD staged floats per 4 outputs), the column pass runs
 // over those 64 columns exactly like the plain kernel, and a step's result is stored only when its source row is picked.
 // Half the row-pass and half the column-pass arithmetic of a full blur, a quarter of the stores.
-struct DecRegion { int k_begin, k_end, parity, first_block; };   // destination columns [k_begin, k_end): source x = 2k + parity
+struct DecRegion { int k_begin, k_end, parity, first_strip; };   // destination columns [k_begin, k_end): source x = 2k + parity; first warp strip of the run
 struct SlideDecArgs {
     BlurArgs a;
-    int seg, ahead, n_regions;
+    int strips;           // warp strips (64 destination columns of one parity run) per image
+    int lanes;
+    uint32_t share, total;   // as SlideArgs
+    int ahead, n_regions;
     DecRegion reg[4];
 };
 
@@ -399,98 +478,121 @@ __global__ void __launch_bounds__(64) blur_slide_dec_kernel(const __grid_constan
     const uint32_t full_u = tma::smem_u32(reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + B::NWARP * warp_floats) + warp * (B::MAX_AHEAD + 1));
 
     const BlurArgs& a = sa.a;
-    const int b = blockIdx.z + a.z0;
     const int w = a.w, h = a.h;
-    int ri = 0;
-    while (ri + 1 < sa.n_regions && (int)blockIdx.x >= sa.reg[ri + 1].first_block) ++ri;
-    const DecRegion rg = sa.reg[ri];
-    // first destination column of this warp; runs start at an even column (the TMA box must start on a 16-byte boundary:
-    // x = 2*k0 - RPAD a multiple of 4), columns below k_begin are computed with the wrong parity and never stored
-    const int k0 = (rg.k_begin & ~1) + (((int)blockIdx.x - rg.first_block) * B::NWARP + warp) * B::WC;
-    if (k0 >= rg.k_end) return;
-    const int xs = 2 * k0;                                  // staged column c holds source x = xs - RPAD + c
-    const int y0 = blockIdx.y * sa.seg;
-    const int y1 = min(y0 + sa.seg, h);
-    const int n_virtual = (y1 - y0) + 2 * R;
-    const int n_chunks = (n_virtual + B::CH - 1) / B::CH;
-    const int v_first = y0 - R;
-    const bool edge = (xs - B::RPAD < 0) || (xs - B::RPAD + C::SWW > w);
-
     if (lane == 0) {
         tma::prefetch_map(&map8);
         for (int s = 0; s < nstg; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_u + 8 * s) : "memory");
         tma::fence_barrier_init();
     }
     __syncwarp();
-    if (lane == 0) {
-        for (int i = 0; i < nstg && i < n_chunks; ++i)
-            sl_issue_chunk(stage_u + i * C::STAGE_FLOATS * 4, full_u + 8 * i, &map8, &map1, xs - B::RPAD, v_first + i * B::CH, h, b, C::SWW);
-    }
     float tk[R + 1];
 #pragma unroll
     for (int j = 0; j <= R; ++j) tk[j] = taps.tk[j];
     const float one = taps.one;
-
     const int cg = lane & 15, rsub = lane >> 4;
+    const float* const mid_lane = mid + 2 * lane;
+
+    const uint32_t gw = blockIdx.x * B::NWARP + warp;
+    const uint32_t row_lane = gw / (uint32_t)sa.strips;
+    if (row_lane >= (uint32_t)sa.lanes) return;
+    const int strip = (int)(gw - row_lane * (uint32_t)sa.strips);
+    int ri = 0;
+    while (ri + 1 < sa.n_regions && strip >= sa.reg[ri + 1].first_strip) ++ri;
+    const DecRegion rg = sa.reg[ri];
+    // first destination column of this strip; runs start at an even column (the TMA box must start on a 16-byte boundary:
+    // x = 2*k0 - RPAD a multiple of 4), columns below k_begin are computed with the wrong parity and never stored
+    const int k0 = (rg.k_begin & ~1) + (strip - rg.first_strip) * B::WC;
+    const int xs = 2 * k0;                                  // staged column c holds source x = xs - RPAD + c
+    const int par = rg.parity;
+    const SlPatch patch = sl_patch_setup(lane, w, xs - B::RPAD, R, C::SWW);
+    const bool edge = __any_sync(0xffffffffu, (patch.left & patch.right) != ~0u);
     const int k = k0 + 2 * lane;                            // this lane's destination columns k, k + 1
     const bool ok0 = k >= rg.k_begin && k < rg.k_end, ok1 = k + 1 >= rg.k_begin && k + 1 < rg.k_end;
-    float* const dst_img = a.dst + (size_t)b * a.dst_stride + k;
-
-    float2 acc[B::NACC];
-#pragma unroll
-    for (int q = 0; q < B::NACC; ++q) acc[q] = make_float2(0.0f, 0.0f);
-
+    uint32_t g = row_lane * sa.share;
+    const uint32_t g_end = min(sa.total, g + sa.share);
     int s = 0;
     uint32_t parity = 0;
-    const float* const mid_lane = mid + 2 * lane;
+    // state of the current piece (one flat loop over the chunks of all pieces, as in blur_slide_kernel)
+    int i = 0, n_chunks = 0, n_virtual = 0, v_first = 0, bz = 0, y_top = 0;
+    float* dst_img = nullptr;
+    float2 acc[B::NACC];
 #pragma unroll 1
-    for (int i = 0; i < n_chunks; ++i) {
-        float* const st = stage + s * C::STAGE_FLOATS;
-        sl_wait(full_u + 8 * s, parity);
-        if (edge) sl_patch_columns(st, B::CH, w, xs, B::RPAD, R, C::SWW, lane);
-        {
-            float wv[2][C::NW];
-            auto load_window = [&](float (&dstw)[C::NW], int rw) {
-                const float* srow = st + rw * C::SWW + 8 * cg;
-#pragma unroll
-                for (int q = 0; q < C::NW / 4; ++q) {
-                    const float4 f = *reinterpret_cast<const float4*>(srow + 4 * q);
-                    dstw[4 * q] = f.x; dstw[4 * q + 1] = f.y; dstw[4 * q + 2] = f.z; dstw[4 * q + 3] = f.w;
+    for (;;) {
+        if (i == n_chunks) {   // next piece
+            if (g >= g_end) break;
+            const uint32_t b = g / (uint32_t)h;
+            const int y0 = (int)(g - b * (uint32_t)h);
+            const int y1 = min(h, y0 + (int)(g_end - g));
+            g += (uint32_t)(y1 - y0);
+            bz = (int)b + a.z0;
+            n_virtual = (y1 - y0) + 2 * R;
+            n_chunks = (n_virtual + B::CH - 1) / B::CH;
+            v_first = y0 - R;
+            y_top = y0 - 2 * R;
+            i = 0;
+            if (lane == 0) {
+                int st = s;
+                for (int q = 0; q < nstg && q < n_chunks; ++q) {
+                    sl_issue_chunk(stage_u + st * C::STAGE_FLOATS * 4, full_u + 8 * st, &map8, &map1, xs - B::RPAD, v_first + q * B::CH, h, bz, C::SWW);
+                    if (++st == nstg) st = 0;
                 }
-            };
-            load_window(wv[0], rsub);
-#pragma unroll
-            for (int q = 0; q < B::CH / 2; ++q) {
-                const int rw = rsub + 2 * q;
-                if (q + 1 < B::CH / 2) load_window(wv[(q + 1) & 1], rw + 2);
-                const float (&wq)[C::NW] = wv[q & 1];
-                const float4 o4 = rg.parity ? sl_dec_outputs<R, FMA, 1>(wq, taps) : sl_dec_outputs<R, FMA, 0>(wq, taps);
-                *reinterpret_cast<float4*>(mid + rw * B::MW + 4 * cg) = o4;
             }
-        }
-        __syncwarp();
-        if (lane == 0 && i + nstg < n_chunks)
-            sl_issue_chunk(stage_u + s * C::STAGE_FLOATS * 4, full_u + 8 * s, &map8, &map1, xs - B::RPAD, v_first + (i + nstg) * B::CH, h, b, C::SWW);
-
-        // column pass: step r consumes virtual row i*8 + r and completes source row yo = y0 - 2R + i*8 + r
-        const int t0 = i * B::CH;
+            dst_img = a.dst + (size_t)bz * a.dst_stride + k;
 #pragma unroll
-        for (int r = 0; r < B::CH; ++r) {
-            const float2 hv = *reinterpret_cast<const float2*>(mid_lane + r * B::MW);
-            const float2 res = sl_col_step<R, FMA>(acc, hv, tk, one);
-            const int t = t0 + r;
-            const int yo = y0 - 2 * R + t;
-            if (t >= 2 * R && t < n_virtual) {               // warp-uniform
-                const int drow = __ldg(a.sel_y + yo);        // destination row of this source row, or -1
-                if (drow >= 0) {
+            for (int q = 0; q < B::NACC; ++q) acc[q] = make_float2(0.0f, 0.0f);
+        }
+        {
+            float* const st = stage + s * C::STAGE_FLOATS;
+            // destination row of each of the chunk's eight completed source rows (lane r holds step r's), fetched before the row
+            // pass so that the load's latency is off the column pass's critical path
+            const int t0 = i * B::CH;
+            int my_drow = -1;
+            {
+                const int t = t0 + lane;
+                if (lane < B::CH && t >= 2 * R && t < n_virtual) my_drow = __ldg(a.sel_y + (y_top + t));
+            }
+            sl_wait(full_u + 8 * s, parity);
+            if (edge) sl_patch_apply<B::CH>(st, patch, C::SWW);
+            {
+                float wv[2][C::NW];
+                auto load_window = [&](float (&dstw)[C::NW], int rw) {
+                    const float* srow = st + rw * C::SWW + 8 * cg;
+#pragma unroll
+                    for (int q = 0; q < C::NW / 4; ++q) {
+                        const float4 f = *reinterpret_cast<const float4*>(srow + 4 * q);
+                        dstw[4 * q] = f.x; dstw[4 * q + 1] = f.y; dstw[4 * q + 2] = f.z; dstw[4 * q + 3] = f.w;
+                    }
+                };
+                load_window(wv[0], rsub);
+#pragma unroll
+                for (int q = 0; q < B::CH / 2; ++q) {
+                    const int rw = rsub + 2 * q;
+                    if (q + 1 < B::CH / 2) load_window(wv[(q + 1) & 1], rw + 2);
+                    const float (&wq)[C::NW] = wv[q & 1];
+                    const float4 o4 = par ? sl_dec_outputs<R, FMA, 1>(wq, taps) : sl_dec_outputs<R, FMA, 0>(wq, taps);
+                    *reinterpret_cast<float4*>(mid + rw * B::MW + 4 * cg) = o4;
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && i + nstg < n_chunks)
+                sl_issue_chunk(stage_u + s * C::STAGE_FLOATS * 4, full_u + 8 * s, &map8, &map1, xs - B::RPAD, v_first + (i + nstg) * B::CH, h, bz, C::SWW);
+
+            // column pass: step r consumes virtual row i*8 + r and completes source row yo = y0 - 2R + i*8 + r
+#pragma unroll
+            for (int r = 0; r < B::CH; ++r) {
+                const float2 hv = *reinterpret_cast<const float2*>(mid_lane + r * B::MW);
+                const float2 res = sl_col_step<R, FMA>(acc, hv, tk, one);
+                const int drow = __shfl_sync(0xffffffffu, my_drow, r);   // -1: not picked, or outside the piece
+                if (drow >= 0) {                                         // warp-uniform
                     float* o = dst_img + (size_t)drow * a.dst_pitch;
                     if (ok0) o[0] = res.x;
                     if (ok1) o[1] = res.y;
                 }
             }
+            __syncwarp();
+            if (++s == nstg) { s = 0; parity ^= 1u; }
+            ++i;
         }
-        __syncwarp();
-        if (++s == nstg) { s = 0; parity ^= 1u; }
     }
 }
 
@@ -518,6 +620,28 @@ int slide_box_width(int r) {   // same for DOG and plain (SWW does not depend on
         case 27: return slide_box_width_r<27>(true);
         default: return 0;
     }
+}
+
+// Grid and share of a launch (see SlideArgs): as many CTAs as the device holds at once, fewer when the level is so small that a
+// share would be mostly vertical halo.  Returns the number of CTAs.
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int slide_partition(int strips, int batch, int h, int R, int nwarp, int n_sm, int cps, int* lanes, uint32_t* share, uint32_t* total) {
+    static const int cps_cap = env_int("SIFT_GPU_SLIDE_CPS", 0);          // development knobs
+    static const int even = env_int("SIFT_GPU_SLIDE_CPS_EVEN", 0);
+    static const int min_mult = env_int("SIFT_GPU_SLIDE_MIN_SHARE", 4);
+    const uint64_t tot = (uint64_t)batch * (uint64_t)h;
+    if (tot >= (1ull << 31) || strips < 1) return -1;
+    if (cps_cap > 0 && cps > cps_cap) cps = cps_cap;
+    if (even && cps > 1 && (cps * nwarp) % 4 != 0) --cps;
+    const uint64_t min_share = (uint64_t)std::max(64, min_mult * (2 * R + 8));
+    uint64_t nl = (uint64_t)n_sm * cps * nwarp / strips;           // row lanes the resident warps can form
+    const uint64_t by_work = std::max<uint64_t>(1, tot / min_share);
+    if (nl > by_work) nl = by_work;
+    if (nl < 1) nl = 1;
+    *lanes = (int)nl;
+    *share = (uint32_t)((tot + nl - 1) / nl);
+    *total = (uint32_t)tot;
+    return (int)((nl * strips + nwarp - 1) / nwarp);
 }
 
 struct SlideDevInfo { bool ready = false; int n_sm = 148; int ahead = 1; int cps[8][2][3] = {}; };   // [radius index][fma][mode]
@@ -593,32 +717,85 @@ static int launch_slide_r(const BlurArgs& a, int batch, bool fma, int idx, cudaS
     }
     SlideArgs sa;
     sa.a = a;
-    // Rows per CTA: more segments = more parallelism but 2R extra rows to stage, row-filter and scatter per segment; fewer
-    // segments = less overhead but a ragged last wave.  Pick the count with the best (last-wave fill) / (overhead).
-    const int strips = (a.w + C::NWARP * C::WC - 1) / (C::NWARP * C::WC);
+    const int strips = (a.w + C::WC - 1) / C::WC;
     const int cps = d.cps[idx][fma ? 1 : 0][mode];
-    static const bool use_share = [] { const char* e = getenv("SIFT_GPU_SLIDE_SHARE"); return e ? atoi(e) != 0 : true; }();
-    const double slots = (double)d.n_sm * cps / (use_share && a.share > 1 ? a.share : 1);
-    int seg = a.h;
-    double best = -1.0;
-    for (int nseg = 1; nseg <= (a.h + 15) / 16; ++nseg) {
-        const int sg = ((a.h + nseg - 1) / nseg + C::CH - 1) / C::CH * C::CH;
-        const int real_segs = (a.h + sg - 1) / sg;
-        const double tiles = (double)strips * real_segs * batch;
-        const double waves = std::ceil(tiles / slots);
-        const double fill = tiles / (waves * slots);
-        const double overhead = (double)(sg + 2 * R + C::CH) / sg;
-        const double score = fill / overhead;
-        if (score > best + 1e-9) { best = score; seg = sg; }
-    }
-    sa.seg = seg;
+    sa.strips = strips;
+    const int ctas = slide_partition(strips, batch, a.h, R, C::NWARP, d.n_sm, cps, &sa.lanes, &sa.share, &sa.total);
+    if (ctas <= 0) return -1;
     sa.ahead = slide_ahead();
-    dim3 grid(strips, (a.h + seg - 1) / seg, batch);
+    dim3 grid(ctas, 1, 1);
+    static const bool probe_on = getenv("SIFT_GPU_SLIDE_PROBE") != nullptr;
+    sa.probe = nullptr;
+    const size_t n_probe = (size_t)ctas * C::NWARP;
+    if (probe_on) {
+        SIFT_CUDA_TRY(cudaMalloc(&sa.probe, n_probe * 4 * sizeof(unsigned long long)));
+        SIFT_CUDA_TRY(cudaMemsetAsync(sa.probe, 0, n_probe * 4 * sizeof(unsigned long long), s));
+    }
 #define SL_LAUNCH(F, M) blur_slide_kernel<R, F, M><<<grid, C::NWARP * 32, SL<R, M != 0>::smem(sa.ahead + 1), s>>>(a.map[0], a.map[1], sa, tp)
     if (fma) { if (mode == 0) SL_LAUNCH(true, 0); else if (mode == 1) SL_LAUNCH(true, 1); else SL_LAUNCH(true, 2); }
     else { if (mode == 0) SL_LAUNCH(false, 0); else if (mode == 1) SL_LAUNCH(false, 1); else SL_LAUNCH(false, 2); }
 #undef SL_LAUNCH
     SIFT_CUDA_TRY(cudaGetLastError());
+    if (probe_on) {
+        std::vector<unsigned long long> hp(n_probe * 4);
+        SIFT_CUDA_TRY(cudaStreamSynchronize(s));
+        SIFT_CUDA_TRY(cudaMemcpy(hp.data(), sa.probe, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(sa.probe);
+        unsigned long long t0 = ~0ull, t1 = 0;
+        for (size_t i = 0; i < n_probe; ++i)
+            if (hp[4 * i + 1]) { t0 = std::min(t0, hp[4 * i]); t1 = std::max(t1, hp[4 * i + 1]); }
+        const double T = (double)(t1 - t0);
+        std::vector<double> sm_end(256, 0.0), sm_start(256, 1e30);
+        std::vector<int> sm_warps(256, 0);
+        double dur_sum = 0, dur_min = 1e30, dur_max = 0, q_dur[4] = {0, 0, 0, 0};
+        int q_n[4] = {0, 0, 0, 0}, n = 0;
+        for (size_t i = 0; i < n_probe; ++i) {
+            if (!hp[4 * i + 1]) continue;
+            const double a0 = (double)(hp[4 * i] - t0), a1 = (double)(hp[4 * i + 1] - t0), dd = a1 - a0;
+            const int sm = (int)hp[4 * i + 2] & 255, q = (int)hp[4 * i + 3] & 3;
+            sm_end[sm] = std::max(sm_end[sm], a1); sm_start[sm] = std::min(sm_start[sm], a0); ++sm_warps[sm];
+            dur_sum += dd; dur_min = std::min(dur_min, dd); dur_max = std::max(dur_max, dd); q_dur[q] += dd; ++q_n[q]; ++n;
+        }
+        if (const char* dump = getenv("SIFT_GPU_SLIDE_PROBE_DUMP")) {
+            if (FILE* f = fopen(dump, "a")) {
+                fprintf(f, "# R=%d mode=%d w=%d h=%d strips=%d lanes=%d share=%u\n", R, mode, a.w, a.h, sa.strips, sa.lanes, sa.share);
+                for (size_t i = 0; i < n_probe; ++i)
+                    if (hp[4 * i + 1]) fprintf(f, "%zu %llu %llu %llu %llu\n", i, hp[4 * i] - t0, hp[4 * i + 1] - t0, hp[4 * i + 2], hp[4 * i + 3]);
+                fclose(f);
+            }
+        }
+        {   // who is slow: by strip position, by row lane, and the slowest warps
+            const int ns = sa.strips;
+            std::vector<double> sd((size_t)ns, 0.0); std::vector<int> sn((size_t)ns, 0);
+            std::vector<std::pair<double, size_t>> all;
+            for (size_t i = 0; i < n_probe; ++i) {
+                if (!hp[4 * i + 1]) continue;
+                const double dd = (double)(hp[4 * i + 1] - hp[4 * i]);
+                sd[i % ns] += dd; ++sn[i % ns];
+                all.push_back(std::make_pair(dd, i));
+            }
+            std::sort(all.begin(), all.end());
+            fprintf(stderr, "   by strip:");
+            for (int k = 0; k < ns; ++k) fprintf(stderr, " %.0f", sd[k] / std::max(1, sn[k]) * 1e-3);
+            fprintf(stderr, "\n   slowest:");
+            for (size_t k = 0; k < 12 && k < all.size(); ++k) {
+                const size_t i = all[all.size() - 1 - k].second;
+                fprintf(stderr, " [%.0fus strip %d lane %d sm %d w %d start %.0f]", all[all.size() - 1 - k].first * 1e-3, (int)(i % ns), (int)(i / ns), (int)hp[4 * i + 2],
+                        (int)hp[4 * i + 3], (double)(hp[4 * i] - t0) * 1e-3);
+            }
+            fprintf(stderr, "\n   deciles:");
+            for (int k = 0; k <= 10; ++k) fprintf(stderr, " %.0f", all[std::min(all.size() - 1, all.size() * k / 10)].first * 1e-3);
+            fprintf(stderr, "\n");
+        }
+        std::vector<double> ends, wcount;
+        for (int i = 0; i < 256; ++i) if (sm_warps[i]) { ends.push_back(sm_end[i] / T); wcount.push_back(sm_warps[i]); }
+        std::sort(ends.begin(), ends.end());
+        fprintf(stderr, "[slide probe R=%d mode=%d %dx%d] span %.1f us, %d warps: duration mean %.1f min %.1f max %.1f us; by warpid%%4: %.1f(%d) %.1f(%d) %.1f(%d) %.1f(%d); SM end/T: min %.2f p25 %.2f med %.2f p75 %.2f max %.2f; warps/SM min %.0f max %.0f\n",
+                R, mode, a.w, a.h, T * 1e-3, n, dur_sum / n * 1e-3, dur_min * 1e-3, dur_max * 1e-3, q_dur[0] / std::max(1, q_n[0]) * 1e-3, q_n[0],
+                q_dur[1] / std::max(1, q_n[1]) * 1e-3, q_n[1], q_dur[2] / std::max(1, q_n[2]) * 1e-3, q_n[2], q_dur[3] / std::max(1, q_n[3]) * 1e-3, q_n[3],
+                ends.front(), ends[ends.size() / 4], ends[ends.size() / 2], ends[3 * ends.size() / 4], ends.back(),
+                *std::min_element(wcount.begin(), wcount.end()), *std::max_element(wcount.begin(), wcount.end()));
+    }
     return 0;
 }
 
@@ -687,7 +864,7 @@ static int launch_slide_dec_r(const BlurArgs& a, int batch, bool fma, int idx, c
     SlideDecArgs sa;
     sa.a = a;
     sa.n_regions = 0;
-    int k = 0, blocks = 0;
+    int k = 0, blocks = 0;   // blocks: warp strips so far
     for (int x = 0; x < a.w; ++x) {
         const int dk = a.sel_x_host[x];
         if (dk < 0) continue;
@@ -697,7 +874,7 @@ static int launch_slide_dec_r(const BlurArgs& a, int batch, bool fma, int idx, c
             if (sa.n_regions) {
                 DecRegion& pr = sa.reg[sa.n_regions - 1];
                 pr.k_end = k;
-                blocks += (pr.k_end - (pr.k_begin & ~1) + B::NWARP * B::WC - 1) / (B::NWARP * B::WC);
+                blocks += (pr.k_end - (pr.k_begin & ~1) + B::WC - 1) / B::WC;
             }
             if (sa.n_regions == 4) return -1;
             sa.reg[sa.n_regions++] = DecRegion{k, k, par, blocks};
@@ -708,7 +885,7 @@ static int launch_slide_dec_r(const BlurArgs& a, int batch, bool fma, int idx, c
     {
         DecRegion& pr = sa.reg[sa.n_regions - 1];
         pr.k_end = k;
-        blocks += (pr.k_end - (pr.k_begin & ~1) + B::NWARP * B::WC - 1) / (B::NWARP * B::WC);
+        blocks += (pr.k_end - (pr.k_begin & ~1) + B::WC - 1) / B::WC;
     }
     for (int y = 0; y < a.h; ++y) {   // rows may be picked in any pattern; only sanity-check the range
         const int dy = a.sel_y_host[y];
@@ -727,23 +904,11 @@ static int launch_slide_dec_r(const BlurArgs& a, int batch, bool fma, int idx, c
         tp.po[m] = make_float2(tkv[2 * m + 1], tkv[2 * m + 2]);
     }
     const int cps = g_dec_cps[dev][idx][fma ? 1 : 0];
-    static const bool use_share = [] { const char* e = getenv("SIFT_GPU_SLIDE_SHARE"); return e ? atoi(e) != 0 : true; }();
-    const double slots = (double)d.n_sm * cps / (use_share && a.share > 1 ? a.share : 1);
-    int seg = a.h;
-    double best = -1.0;
-    for (int nseg = 1; nseg <= (a.h + 15) / 16; ++nseg) {
-        const int sg = ((a.h + nseg - 1) / nseg + B::CH - 1) / B::CH * B::CH;
-        const int real_segs = (a.h + sg - 1) / sg;
-        const double tiles = (double)blocks * real_segs * batch;
-        const double waves = std::ceil(tiles / slots);
-        const double fill = tiles / (waves * slots);
-        const double overhead = (double)(sg + 2 * R + B::CH) / sg;
-        const double score = fill / overhead;
-        if (score > best + 1e-9) { best = score; seg = sg; }
-    }
-    sa.seg = seg;
+    sa.strips = blocks;
+    const int ctas = slide_partition(blocks, batch, a.h, R, B::NWARP, d.n_sm, cps, &sa.lanes, &sa.share, &sa.total);
+    if (ctas <= 0) return -1;
     sa.ahead = slide_ahead();
-    dim3 grid(blocks, (a.h + seg - 1) / seg, batch);
+    dim3 grid(ctas, 1, 1);
     if (fma) blur_slide_dec_kernel<R, true><<<grid, 64, SLD<R>::smem(sa.ahead + 1), s>>>(a.map[0], a.map[1], sa, tp);
     else blur_slide_dec_kernel<R, false><<<grid, 64, SLD<R>::smem(sa.ahead + 1), s>>>(a.map[0], a.map[1], sa, tp);
     SIFT_CUDA_TRY(cudaGetLastError());
