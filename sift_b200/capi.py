@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsift_gpu.so")
+LIB_PATH = os.environ.get("SIFT_GPU_LIB") or os.path.join(_HERE, "libsift_gpu.so")   # SIFT_GPU_LIB: development builds of the same ABI
 
 OK, E_INVALID, E_CUDA, E_PRECONDITION, E_CAPACITY, E_ASSERT, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 FLAG_ORDER_CANONICAL, FLAG_STRICT, FLAG_FMA_BLUR, FLAG_KEEP_UPSAMPLED, FLAG_SERIAL = 1, 2, 4, 8, 16

@@ -13,15 +13,41 @@ namespace siftgpu {
 
 constexpr int kExThreads = 128;
 
-// (A) one launch over every scan layer of the pass; CTA = 128 columns x 32 rows of one layer, thread = column x.
-// Rows are taken four at a time: all loads of the block are issued before any of them is used.  "Some neighbour is
-// greater than v" is max(neighbours) > v, and the maximum over the 2 x 2 x 3 block is built from per-row maxima that
-// are carried from row to row (fmaxf/fminf skip NaNs exactly like the chain of ordered compares they replace).
+// (A) one launch over every scan layer of the pass; CTA = 512 columns x 32 rows of one layer, thread = 4 adjacent columns
+// (one 16-byte load per layer and row; the first version read 7 scalars per pixel and was bound by the load unit, not by
+// HBM).  Rows are taken four at a time: all loads of the block are issued before any of them is used.  "Some neighbour is
+// greater than v" is max(neighbours) > v; the maximum over the 2 x 2 x 3 block is built from per-column maxima over the
+// three layers (the left neighbour's comes from the lane to the left by shuffle, a warp's first lane loads its halo column)
+// that are carried from row to row (fmaxf/fminf skip NaNs exactly like the chain of ordered compares they replace).
 // PREFILTER: the two tests of _eliminateEdgeResponses that need no linear algebra (det < 0, edge ratio; sift.cpp:335-344,
 // same expressions as eliminate.cu) only read the 3x3 neighbourhood of the middle layer, which streams through this
 // kernel anyway (one row of look-ahead, one more column).  Candidates that fail them are marked in a second bit plane and
 // come out of the emit kernel already filtered, so the elimination kernel gathers 19 DoG values only for the ~15 % that
 // are left instead of re-reading most of the DoG pyramid sector by sector.
+constexpr int kMaskCols = 4 * kExThreads;   // columns per CTA of the mask kernel
+
+__device__ __forceinline__ float ex_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float ex_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// sift.cpp:335-344 on the middle layer's 3x3 neighbourhood (u = row above, c = this row, d = row below; l / m / r columns)
+__device__ __forceinline__ bool ex_cheap_tests_pass(float ul, float um, float ur, float cl, float cm, float cr, float dl, float dm, float dr) {
+    (void)ul; (void)ur;
+    // algorithms.cpp:82-92
+    const float dxx = cr + cl - 2 * cm;
+    const float dyy = dm + um - 2 * cm;
+    const float dxy = (dr - dl - ur + ul) / 2;
+    const float t = (float)(121.0 / 10);
+    const float tr = dxx + dyy;
+    const float det = (float)((double)(dxx * dyy) - (double)dxy * (double)dxy);
+    if (det < 0) return false;
+    // tr^2 and t*det are exact in double (24-bit factors), so the quotient's side of t is known without the division unless it
+    // lies within rounding distance of t (or det is 0 / NaN): divide only then
+    const double a = (double)tr * (double)tr, bq = (double)t * (double)det;
+    if (det > 0 && a > bq * (1.0 + 1e-12)) return false;
+    if (det > 0 && a <= bq) return true;
+    return !(a / (double)det > (double)t);
+}
+
 template <bool PREFILTER>
 __global__ void __launch_bounds__(kExThreads) extrema_mask_kernel(const ScanLayer* __restrict__ layers, int n_layers, uint32_t* __restrict__ mask,
                                                                   uint32_t* __restrict__ pass_mask, uint32_t mask_words_per_image) {
@@ -30,94 +56,109 @@ __global__ void __launch_bounds__(kExThreads) extrema_mask_kernel(const ScanLaye
     const ScanLayer L = layers[li];
     const int tile = (int)(blockIdx.x - L.tile_base);
     const int yw = tile / (int)L.tiles_x;
-    const int x = (tile - yw * (int)L.tiles_x) * kExThreads + threadIdx.x;
+    const int x0 = (tile - yw * (int)L.tiles_x) * kMaskCols + 4 * (int)threadIdx.x;   // this thread's columns x0 .. x0 + 3
     const int b = blockIdx.y;
-    if (x >= L.w) return;
+    const int lane = threadIdx.x & 31;
+    // a warp whose 128 columns all lie beyond the image leaves (the shuffles below need whole warps)
+    if (x0 - 4 * lane >= L.w) return;
+    const bool in_row = x0 < L.w;                    // lanes beyond the last column only take part in the shuffles
     const size_t img = (size_t)b * L.stride;
-    const float* d1 = L.d1 + img + x;  // middle layer
-    const float* d0 = L.d0 + img + x;
-    const float* d2 = L.d2 + img + x;
-    const int pitch = L.pitch, h = L.h;
-    uint32_t word = 0, pass = 0;
-    if (x >= 1 && x <= L.w - 2) {
-        const int ybeg = yw * 32;
-        // carried from the previous row: max / min over the 6 values (x-1, x) x 3 layers, and the middle layer's 3 values
-        float pmax, pmin, pl1, pc1, pr1 = 0.0f;
-        {
-            const size_t o = (size_t)(ybeg - 1 < 0 ? 0 : ybeg - 1) * pitch;
-            const float a0 = d0[o - 1], a1 = d0[o], b0 = d1[o - 1], b1 = d1[o], c0 = d2[o - 1], c1 = d2[o];
-            pmax = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)), fmaxf(c0, c1));
-            pmin = fminf(fminf(fminf(a0, a1), fminf(b0, b1)), fminf(c0, c1));
-            pl1 = b0; pc1 = b1;
-            if (PREFILTER) pr1 = d1[o + 1];
+    const int xl = in_row ? x0 : 0;                  // a safe column for those lanes
+    const float* d0 = L.d0 + img + xl;
+    const float* d1 = L.d1 + img + xl;               // middle layer
+    const float* d2 = L.d2 + img + xl;
+    const int pitch = L.pitch, h = L.h, w = L.w;
+    const bool halo_l = lane == 0 && x0 > 0;          // first lane: column x0 - 1 comes from memory
+    const bool halo_r = PREFILTER && in_row && (lane == 31 || x0 + 4 >= w) && x0 + 4 < pitch;   // last lane: column x0 + 4 of the middle layer
+    uint32_t word[4] = {0, 0, 0, 0}, pass[4] = {0, 0, 0, 0};
+    const int ybeg = yw * 32;
+
+    // one row of the three layers at this thread's columns -> per-column max / min over the layers (index 0 = column x0 - 1)
+    float pmax[5], pmin[5];   // previous row
+    float p1[6];              // previous row of the middle layer, columns x0 - 1 .. x0 + 4 (PREFILTER)
+    auto column_extremes = [&](const float4& a, const float4& m, const float4& c, float hl0, float hl1, float hl2, float (&mx)[5], float (&mn)[5]) {
+        mx[1] = ex_max3(a.x, m.x, c.x); mx[2] = ex_max3(a.y, m.y, c.y); mx[3] = ex_max3(a.z, m.z, c.z); mx[4] = ex_max3(a.w, m.w, c.w);
+        mn[1] = ex_min3(a.x, m.x, c.x); mn[2] = ex_min3(a.y, m.y, c.y); mn[3] = ex_min3(a.z, m.z, c.z); mn[4] = ex_min3(a.w, m.w, c.w);
+        const float lmx = __shfl_up_sync(0xffffffffu, mx[4], 1), lmn = __shfl_up_sync(0xffffffffu, mn[4], 1);
+        mx[0] = halo_l ? ex_max3(hl0, hl1, hl2) : lmx;
+        mn[0] = halo_l ? ex_min3(hl0, hl1, hl2) : lmn;
+    };
+    auto middle_row = [&](const float4& m, float hl1, float hr1, float (&r)[6]) {
+        const float fl = __shfl_up_sync(0xffffffffu, m.w, 1), fr = __shfl_down_sync(0xffffffffu, m.x, 1);
+        r[0] = halo_l ? hl1 : fl; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = m.w; r[5] = halo_r ? hr1 : fr;
+    };
+    {
+        const size_t o = (size_t)(ybeg - 1 < 0 ? 0 : ybeg - 1) * pitch;
+        const float4 a = *reinterpret_cast<const float4*>(d0 + o), m = *reinterpret_cast<const float4*>(d1 + o), c = *reinterpret_cast<const float4*>(d2 + o);
+        float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, hr = 0.0f;
+        if (halo_l) { h0 = d0[o - 1]; h1 = d1[o - 1]; h2 = d2[o - 1]; }
+        if (halo_r) hr = d1[o + 4];
+        column_extremes(a, m, c, h0, h1, h2, pmax, pmin);
+        if (PREFILTER) middle_row(m, h1, hr, p1);
+    }
+    constexpr int RB = 4;
+    for (int k0 = 0; k0 < 32 && ybeg + k0 < h; k0 += RB) {
+        float4 va[RB], vm[RB + 1], vc[RB];
+        float hl0[RB], hl1[RB + 1], hl2[RB], hr1[RB + 1];
+#pragma unroll
+        for (int q = 0; q < RB + (PREFILTER ? 1 : 0); ++q) {   // one row of look-ahead on the middle layer for the prefilter
+            const int y = ybeg + k0 + q;
+            const size_t o = (size_t)(y < h ? y : h - 1) * pitch;
+            vm[q] = *reinterpret_cast<const float4*>(d1 + o);
+            hl1[q] = halo_l ? d1[o - 1] : 0.0f;
+            hr1[q] = halo_r ? d1[o + 4] : 0.0f;
+            if (q < RB) {
+                va[q] = *reinterpret_cast<const float4*>(d0 + o);
+                vc[q] = *reinterpret_cast<const float4*>(d2 + o);
+                hl0[q] = halo_l ? d0[o - 1] : 0.0f;
+                hl2[q] = halo_l ? d2[o - 1] : 0.0f;
+            }
         }
-        constexpr int RB = 4;
-        for (int k0 = 0; k0 < 32 && ybeg + k0 < h; k0 += RB) {
-            float v0l[RB], v0c[RB], v1l[RB], v1c[RB], v1r[RB], v2l[RB], v2c[RB];
+        float c1[6], n1[6];   // middle layer: this row, next row
+        if (PREFILTER) middle_row(vm[0], hl1[0], hr1[0], c1);
 #pragma unroll
-            for (int q = 0; q < RB; ++q) {
-                const int y = ybeg + k0 + q;
-                const size_t o = (size_t)(y < h ? y : h - 1) * pitch;
-                v0l[q] = d0[o - 1]; v0c[q] = d0[o];
-                v1l[q] = d1[o - 1]; v1c[q] = d1[o];
-                v2l[q] = d2[o - 1]; v2c[q] = d2[o];
-                if (PREFILTER) v1r[q] = d1[o + 1];
-            }
-            float nl = 0.0f, nc = 0.0f, nr = 0.0f;  // middle layer, first row after this block (look-ahead of the last row)
-            if (PREFILTER) {
-                const int y = ybeg + k0 + RB;
-                const size_t o = (size_t)(y < h ? y : h - 1) * pitch;
-                nl = d1[o - 1]; nc = d1[o]; nr = d1[o + 1];
-            }
+        for (int q = 0; q < RB; ++q) {
+            const int y = ybeg + k0 + q;
+            float cmax[5], cmin[5];
+            column_extremes(va[q], vm[q], vc[q], hl0[q], hl1[q], hl2[q], cmax, cmin);
+            if (PREFILTER) middle_row(vm[q + 1], hl1[q + 1], hr1[q + 1], n1);
+            const float v[4] = {vm[q].x, vm[q].y, vm[q].z, vm[q].w};
+            const bool row_ok = y >= 1 && y <= h - 2;
 #pragma unroll
-            for (int q = 0; q < RB; ++q) {
-                const int y = ybeg + k0 + q;
-                const float cmax = fmaxf(fmaxf(fmaxf(v0l[q], v0c[q]), fmaxf(v1l[q], v1c[q])), fmaxf(v2l[q], v2c[q]));
-                const float cmin = fminf(fminf(fminf(v0l[q], v0c[q]), fminf(v1l[q], v1c[q])), fminf(v2l[q], v2c[q]));
-                const float v = v1c[q];
-                const bool gt = fmaxf(pmax, cmax) > v, lt = fminf(pmin, cmin) < v;
-                if ((!gt || !lt) && y >= 1 && y <= h - 2) {
-                    word |= 1u << (k0 + q);
-                    if (PREFILTER) {
-                        // algorithms.cpp:82-92 on the middle layer, then sift.cpp:335-344
-                        const float dn_l = q + 1 < RB ? v1l[q + 1 < RB ? q + 1 : q] : nl;
-                        const float dn_c = q + 1 < RB ? v1c[q + 1 < RB ? q + 1 : q] : nc;
-                        const float dn_r = q + 1 < RB ? v1r[q + 1 < RB ? q + 1 : q] : nr;
-                        const float c11 = v;
-                        const float dxx = v1r[q] + v1l[q] - 2 * c11;
-                        const float dyy = dn_c + pc1 - 2 * c11;
-                        const float dxy = (dn_r - dn_l - pr1 + pl1) / 2;
-                        const float t = (float)(121.0 / 10);
-                        const float tr = dxx + dyy;
-                        const float det = (float)((double)(dxx * dyy) - (double)dxy * (double)dxy);
-                        bool filtered = false;
-                        if (det < 0) filtered = true;
-                        else {
-                            // tr^2 and t*det are exact in double (24-bit factors), so the quotient's side of t is known without
-                            // the division unless it lies within rounding distance of t (or det is 0 / NaN): divide only then
-                            const double a = (double)tr * (double)tr, bq = (double)t * (double)det;
-                            if (det > 0 && a > bq * (1.0 + 1e-12)) filtered = true;
-                            else if (det > 0 && a <= bq) filtered = false;
-                            else if (a / (double)det > (double)t) filtered = true;
-                        }
-                        if (!filtered) pass |= 1u << (k0 + q);
-                    }
+            for (int j = 0; j < 4; ++j) {
+                const float mx = fmaxf(fmaxf(pmax[j], pmax[j + 1]), fmaxf(cmax[j], cmax[j + 1]));
+                const float mn = fminf(fminf(pmin[j], pmin[j + 1]), fminf(cmin[j], cmin[j + 1]));
+                const bool gt = mx > v[j], lt = mn < v[j];
+                const int x = x0 + j;
+                if ((!gt || !lt) && row_ok && in_row && x >= 1 && x <= w - 2) {
+                    word[j] |= 1u << (k0 + q);
+                    if (PREFILTER && ex_cheap_tests_pass(p1[j], p1[j + 1], p1[j + 2], c1[j], c1[j + 1], c1[j + 2], n1[j], n1[j + 1], n1[j + 2]))
+                        pass[j] |= 1u << (k0 + q);
                 }
-                pmax = cmax; pmin = cmin;
-                pl1 = v1l[q]; pc1 = v1c[q];
-                if (PREFILTER) pr1 = v1r[q];
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { pmax[j] = cmax[j]; pmin[j] = cmin[j]; }
+            if (PREFILTER) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { p1[j] = c1[j]; c1[j] = n1[j]; }
             }
         }
     }
-    const size_t at = (size_t)b * mask_words_per_image + L.mask_off + (size_t)yw * L.w + x;
-    mask[at] = word;
-    if (PREFILTER) pass_mask[at] = pass;
+    if (in_row) {
+        const size_t at = (size_t)b * mask_words_per_image + L.mask_off + (size_t)yw * w + x0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x0 + j < w) {
+                mask[at + j] = word[j];
+                if (PREFILTER) pass_mask[at + j] = pass[j];
+            }
+    }
 }
 
 void set_scan_tiles(ScanLayer* layers, int n_layers) {
     uint32_t base = 0;
     for (int l = 0; l < n_layers; ++l) {
-        layers[l].tiles_x = (uint32_t)((layers[l].w + kExThreads - 1) / kExThreads);
+        layers[l].tiles_x = (uint32_t)((layers[l].w + kMaskCols - 1) / kMaskCols);
         layers[l].tile_base = base;
         base += layers[l].tiles_x * (uint32_t)layers[l].n_yw;
     }

@@ -1523,9 +1523,14 @@ struct DebugLayers {
 static int debug_layers_setup(sift_gpu_ctx* c, DebugLayers& S, const float* d0, const float* d1, const float* d2, int w, int h) {
     const float* hs[3] = {d0, d1, d2};
     const size_t n = level_px(w, h);
-    for (int i = 0; i < 3; ++i) CTX_TRY(upload(c, hs[i], n, &S.d[i]));
+    const int pitch = pitch_of(w);   // the kernels read rows 16 bytes at a time: same row pitch rule as the pyramid levels
+    for (int i = 0; i < 3; ++i) {
+        CTX_CUDA(cudaMalloc(&S.d[i], sizeof(float) * level_px(pitch, h)));
+        CTX_CUDA(cudaMemset(S.d[i], 0, sizeof(float) * level_px(pitch, h)));
+        CTX_CUDA(cudaMemcpy2D(S.d[i], sizeof(float) * (size_t)pitch, hs[i], sizeof(float) * (size_t)w, sizeof(float) * (size_t)w, (size_t)h, cudaMemcpyHostToDevice));
+    }
     S.L.d0 = S.d[0]; S.L.d1 = S.d[1]; S.L.d2 = S.d[2];
-    S.L.stride = 0; S.L.pitch = w; S.L.w = w; S.L.h = h; S.L.n_yw = (h + 31) / 32; S.L.mask_off = 0; S.L.col_base = 0; S.L.octave = 0; S.L.index = 1;
+    S.L.stride = 0; S.L.pitch = pitch; S.L.w = w; S.L.h = h; S.L.n_yw = (h + 31) / 32; S.L.mask_off = 0; S.L.col_base = 0; S.L.octave = 0; S.L.index = 1;
     set_scan_tiles(&S.L, 1);
     CTX_CUDA(cudaMalloc(&S.dev, sizeof(ScanLayer)));
     CTX_CUDA(cudaMemcpy(S.dev, &S.L, sizeof(ScanLayer), cudaMemcpyHostToDevice));

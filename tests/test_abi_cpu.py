@@ -252,3 +252,62 @@ def test_jpeg_front_end_library_exports_its_header(built):
         sift = capi.SiftGpu(3, 3, max_width=64, max_height=64)
     assert sift is None
 
+
+
+def _host_lib():
+    import ctypes
+
+    lib = ctypes.CDLL(os.path.join(ROOT, "sift_b200", "libsift_host.so"))
+    lib.sift_host_read_image.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_int]
+    lib.sift_host_read_image.restype = ctypes.c_int
+    lib.sift_host_write_png.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.sift_host_write_png.restype = ctypes.c_int
+    return lib
+
+
+def _read_image(lib, path):
+    import ctypes
+
+    w, h = ctypes.c_int(0), ctypes.c_int(0)
+    err = ctypes.create_string_buffer(256)
+    if lib.sift_host_read_image(str(path).encode(), None, ctypes.byref(w), ctypes.byref(h), err, 256) != 0:
+        raise ValueError(err.value.decode())
+    px = np.zeros((h.value, w.value, 3), np.uint8)
+    assert lib.sift_host_read_image(str(path).encode(), px.ctypes.data, ctypes.byref(w), ctypes.byref(h), err, 256) == 0
+    return px
+
+
+def test_cli_image_files_png_and_pnm(built, tmp_path):
+    """main.cpp:52-54 / :59: the shim's own PNG reader (all five scanline filters, grey / RGB / RGBA / palette) and the PNM
+    reader give the pixels PIL gives; the overlay writer (main.cpp:76) produces a PNG PIL reads back unchanged."""
+    from PIL import Image
+
+    lib = _host_lib()
+    rng = np.random.default_rng(3)
+    h, w = 37, 53
+    smooth = (np.add.outer(np.arange(h) * 3, np.arange(w) * 2) % 256).astype(np.uint8)      # makes PIL pick Sub/Up/Average/Paeth
+    rgb = np.stack([smooth, rng.integers(0, 256, (h, w)).astype(np.uint8), smooth[::-1]], axis=2)
+    cases = {"rgb": Image.fromarray(rgb, "RGB"), "grey": Image.fromarray(smooth, "L"), "rgba": Image.fromarray(np.dstack([rgb, smooth]), "RGBA"),
+             "palette": Image.fromarray(rgb, "RGB").quantize(17), "grey_alpha": Image.fromarray(np.dstack([smooth, smooth[:, ::-1]]), "LA")}
+    for name, im in cases.items():
+        p = tmp_path / f"{name}.png"
+        im.save(p, optimize=(name == "rgb"))
+        want = np.asarray(im.convert("RGB"))
+        assert np.array_equal(_read_image(lib, p), want), name
+    # binary PGM / PPM
+    (tmp_path / "g.pgm").write_bytes(b"P5\n# comment\n53 37\n255\n" + smooth.tobytes())
+    (tmp_path / "c.ppm").write_bytes(b"P6 53 37 255\n" + rgb.tobytes())
+    assert np.array_equal(_read_image(lib, tmp_path / "g.pgm"), np.repeat(smooth[:, :, None], 3, 2))
+    assert np.array_equal(_read_image(lib, tmp_path / "c.ppm"), rgb)
+    # writer
+    out = tmp_path / "out.png"
+    assert lib.sift_host_write_png(str(out).encode(), rgb.ctypes.data, w, h) == 0
+    assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), rgb)
+    assert np.array_equal(_read_image(lib, out), rgb)
+    # not an image / unsupported: an error message, no crash
+    (tmp_path / "x.txt").write_bytes(b"hello world, not an image")
+    with pytest.raises(ValueError):
+        _read_image(lib, tmp_path / "x.txt")
+    Image.fromarray(rgb, "RGB").save(tmp_path / "i.png", interlace=True) if False else None
+    with pytest.raises(ValueError):
+        _read_image(lib, tmp_path / "missing.png")

@@ -381,8 +381,42 @@ def test_cli_text_output_equals_oracle_text(built, parrot, tmp_path):
     o = ol.Oracle(3, 4, 1.6, K, False)
     o.calculate(parrot)
     assert open(out).read() == o.text()
-    # main.cpp:59-76: the overlay image is written next to the input
-    ov = open(str(pgm) + "_orientation.ppm", "rb").read()
-    assert ov.startswith(b"P6\n488 600\n255\n")
-    px = np.frombuffer(ov[len(b"P6\n488 600\n255\n"):], np.uint8).reshape(600, 488, 3)
+    # main.cpp:59-76: the overlay image is written next to the input, as <image>_orientation.png
+    from PIL import Image
+
+    px = np.asarray(Image.open(str(pgm) + "_orientation.png").convert("RGB"))
+    assert px.shape == (600, 488, 3)
     assert int(np.all(px == np.array([0, 0, 255], np.uint8), axis=2).sum()) > 1507  # every keypoint left an outline
+
+
+def test_cli_reads_jpeg_and_png_band0(built, parrot, tmp_path):
+    """`./sift example/parrot.jpg -r 1` (reference README): JPEG and PNG files go through the shim's own readers, band 0 feeds
+    the pipeline (main.cpp:52-54).  JPEG decoders differ by a grey level here and there, so the check is against the oracle run
+    on the plane the shim decoded (the same rule as the nvJPEG front end's test)."""
+    import ctypes
+
+    from PIL import Image
+
+    rgb = np.stack([parrot.astype(np.uint8), np.roll(parrot, 7, 1).astype(np.uint8), np.flipud(parrot).astype(np.uint8)], axis=2)
+    lib = ctypes.CDLL(os.path.join(ROOT, "sift_b200", "libsift_host.so"))
+    lib.sift_host_read_image.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_int]
+    for ext, kw in (("png", {}), ("jpg", {"quality": 95, "subsampling": 0})):
+        f = tmp_path / f"parrot.{ext}"
+        Image.fromarray(rgb, "RGB").save(f, **kw)
+        w, h = ctypes.c_int(0), ctypes.c_int(0)
+        err = ctypes.create_string_buffer(256)
+        dec = np.zeros((600, 488, 3), np.uint8)
+        assert lib.sift_host_read_image(str(f).encode(), dec.ctypes.data, ctypes.byref(w), ctypes.byref(h), err, 256) == 0, err.value
+        assert (w.value, h.value) == (488, 600)
+        band0 = dec[:, :, 0].astype(np.float32)
+        if ext == "png":
+            assert np.array_equal(band0, parrot)                       # lossless: band 0 is the R channel
+        else:
+            assert np.abs(band0 - parrot).mean() < 2.0                   # lossy, but the same picture
+        out = tmp_path / f"sift_{ext}.txt"
+        p = subprocess.run([os.path.join(ROOT, "sift_b200", "sift"), str(f), "-r", "1", "--out", str(out)], capture_output=True, text=True)
+        assert p.returncode == 0 and "interest points" in p.stdout, p.stderr
+        o = ol.Oracle(3, 4, 1.6, K, False)
+        o.calculate(band0)
+        assert open(out).read() == o.text(), ext
+        assert os.path.exists(str(f) + "_orientation.png")
