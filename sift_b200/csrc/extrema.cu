@@ -24,14 +24,14 @@ constexpr int kExThreads = 128;
 // kernel anyway (one row of look-ahead, one more column).  Candidates that fail them are marked in a second bit plane and
 // come out of the emit kernel already filtered, so the elimination kernel gathers 19 DoG values only for the ~15 % that
 // are left instead of re-reading most of the DoG pyramid sector by sector.
-constexpr int kMaskCols = 4 * kExThreads;   // columns per CTA of the mask kernel
+constexpr int kMaskWarpCols = 124;                          // output columns per warp: its 32 lanes load 128 columns, the first 4 are the left halo
+constexpr int kMaskCols = (kExThreads / 32) * kMaskWarpCols;   // columns per CTA of the mask kernel
 
 __device__ __forceinline__ float ex_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 __device__ __forceinline__ float ex_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
 // sift.cpp:335-344 on the middle layer's 3x3 neighbourhood (u = row above, c = this row, d = row below; l / m / r columns)
 __device__ __forceinline__ bool ex_cheap_tests_pass(float ul, float um, float ur, float cl, float cm, float cr, float dl, float dm, float dr) {
-    (void)ul; (void)ur;
     // algorithms.cpp:82-92
     const float dxx = cr + cl - 2 * cm;
     const float dyy = dm + um - 2 * cm;
@@ -56,72 +56,53 @@ __global__ void __launch_bounds__(kExThreads) extrema_mask_kernel(const ScanLaye
     const ScanLayer L = layers[li];
     const int tile = (int)(blockIdx.x - L.tile_base);
     const int yw = tile / (int)L.tiles_x;
-    const int x0 = (tile - yw * (int)L.tiles_x) * kMaskCols + 4 * (int)threadIdx.x;   // this thread's columns x0 .. x0 + 3
-    const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    // a warp whose 128 columns all lie beyond the image leaves (the shuffles below need whole warps)
-    if (x0 - 4 * lane >= L.w) return;
-    const bool in_row = x0 < L.w;                    // lanes beyond the last column only take part in the shuffles
+    // this thread's columns x0 .. x0 + 3; a warp's first lane holds the four columns to the left of the warp's outputs (only its
+    // last one is needed, as the left neighbour of the second lane's first column): one aligned 16-byte load like the others
+    // instead of a scalar halo load per layer and row
+    const int xw = (tile - yw * (int)L.tiles_x) * kMaskCols + (int)(threadIdx.x >> 5) * kMaskWarpCols;   // first output column of the warp
+    const int x0 = xw + 4 * lane - 4;
+    const int b = blockIdx.y;
+    if (xw >= L.w) return;                           // whole warps only: the shuffles below need every lane
+    const bool in_row = x0 >= 0 && x0 < L.w && lane > 0;   // lanes that own output columns
     const size_t img = (size_t)b * L.stride;
-    const int xl = in_row ? x0 : 0;                  // a safe column for those lanes
+    const int xl = (x0 >= 0 && x0 < L.w) ? x0 : 0;   // a safe column for the others
     const float* d0 = L.d0 + img + xl;
     const float* d1 = L.d1 + img + xl;               // middle layer
     const float* d2 = L.d2 + img + xl;
     const int pitch = L.pitch, h = L.h, w = L.w;
-    const bool halo_l = lane == 0 && x0 > 0;          // first lane: column x0 - 1 comes from memory
-    const bool halo_r = PREFILTER && in_row && (lane == 31 || x0 + 4 >= w) && x0 + 4 < pitch;   // last lane: column x0 + 4 of the middle layer
-    uint32_t word[4] = {0, 0, 0, 0}, pass[4] = {0, 0, 0, 0};
+    uint32_t word[4] = {0, 0, 0, 0};
     const int ybeg = yw * 32;
 
     // one row of the three layers at this thread's columns -> per-column max / min over the layers (index 0 = column x0 - 1)
     float pmax[5], pmin[5];   // previous row
-    float p1[6];              // previous row of the middle layer, columns x0 - 1 .. x0 + 4 (PREFILTER)
-    auto column_extremes = [&](const float4& a, const float4& m, const float4& c, float hl0, float hl1, float hl2, float (&mx)[5], float (&mn)[5]) {
+    auto column_extremes = [&](const float4& a, const float4& m, const float4& c, float (&mx)[5], float (&mn)[5]) {
         mx[1] = ex_max3(a.x, m.x, c.x); mx[2] = ex_max3(a.y, m.y, c.y); mx[3] = ex_max3(a.z, m.z, c.z); mx[4] = ex_max3(a.w, m.w, c.w);
         mn[1] = ex_min3(a.x, m.x, c.x); mn[2] = ex_min3(a.y, m.y, c.y); mn[3] = ex_min3(a.z, m.z, c.z); mn[4] = ex_min3(a.w, m.w, c.w);
-        const float lmx = __shfl_up_sync(0xffffffffu, mx[4], 1), lmn = __shfl_up_sync(0xffffffffu, mn[4], 1);
-        mx[0] = halo_l ? ex_max3(hl0, hl1, hl2) : lmx;
-        mn[0] = halo_l ? ex_min3(hl0, hl1, hl2) : lmn;
-    };
-    auto middle_row = [&](const float4& m, float hl1, float hr1, float (&r)[6]) {
-        const float fl = __shfl_up_sync(0xffffffffu, m.w, 1), fr = __shfl_down_sync(0xffffffffu, m.x, 1);
-        r[0] = halo_l ? hl1 : fl; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = m.w; r[5] = halo_r ? hr1 : fr;
+        mx[0] = __shfl_up_sync(0xffffffffu, mx[4], 1);   // (lane 0 gets its own value back: it owns no output)
+        mn[0] = __shfl_up_sync(0xffffffffu, mn[4], 1);
     };
     {
         const size_t o = (size_t)(ybeg - 1 < 0 ? 0 : ybeg - 1) * pitch;
         const float4 a = *reinterpret_cast<const float4*>(d0 + o), m = *reinterpret_cast<const float4*>(d1 + o), c = *reinterpret_cast<const float4*>(d2 + o);
-        float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, hr = 0.0f;
-        if (halo_l) { h0 = d0[o - 1]; h1 = d1[o - 1]; h2 = d2[o - 1]; }
-        if (halo_r) hr = d1[o + 4];
-        column_extremes(a, m, c, h0, h1, h2, pmax, pmin);
-        if (PREFILTER) middle_row(m, h1, hr, p1);
+        column_extremes(a, m, c, pmax, pmin);
     }
     constexpr int RB = 4;
     for (int k0 = 0; k0 < 32 && ybeg + k0 < h; k0 += RB) {
-        float4 va[RB], vm[RB + 1], vc[RB];
-        float hl0[RB], hl1[RB + 1], hl2[RB], hr1[RB + 1];
+        float4 va[RB], vm[RB], vc[RB];
 #pragma unroll
-        for (int q = 0; q < RB + (PREFILTER ? 1 : 0); ++q) {   // one row of look-ahead on the middle layer for the prefilter
+        for (int q = 0; q < RB; ++q) {
             const int y = ybeg + k0 + q;
             const size_t o = (size_t)(y < h ? y : h - 1) * pitch;
+            va[q] = *reinterpret_cast<const float4*>(d0 + o);
             vm[q] = *reinterpret_cast<const float4*>(d1 + o);
-            hl1[q] = halo_l ? d1[o - 1] : 0.0f;
-            hr1[q] = halo_r ? d1[o + 4] : 0.0f;
-            if (q < RB) {
-                va[q] = *reinterpret_cast<const float4*>(d0 + o);
-                vc[q] = *reinterpret_cast<const float4*>(d2 + o);
-                hl0[q] = halo_l ? d0[o - 1] : 0.0f;
-                hl2[q] = halo_l ? d2[o - 1] : 0.0f;
-            }
+            vc[q] = *reinterpret_cast<const float4*>(d2 + o);
         }
-        float c1[6], n1[6];   // middle layer: this row, next row
-        if (PREFILTER) middle_row(vm[0], hl1[0], hr1[0], c1);
 #pragma unroll
         for (int q = 0; q < RB; ++q) {
             const int y = ybeg + k0 + q;
             float cmax[5], cmin[5];
-            column_extremes(va[q], vm[q], vc[q], hl0[q], hl1[q], hl2[q], cmax, cmin);
-            if (PREFILTER) middle_row(vm[q + 1], hl1[q + 1], hr1[q + 1], n1);
+            column_extremes(va[q], vm[q], vc[q], cmax, cmin);
             const float v[4] = {vm[q].x, vm[q].y, vm[q].z, vm[q].w};
             const bool row_ok = y >= 1 && y <= h - 2;
 #pragma unroll
@@ -130,28 +111,42 @@ __global__ void __launch_bounds__(kExThreads) extrema_mask_kernel(const ScanLaye
                 const float mn = fminf(fminf(pmin[j], pmin[j + 1]), fminf(cmin[j], cmin[j + 1]));
                 const bool gt = mx > v[j], lt = mn < v[j];
                 const int x = x0 + j;
-                if ((!gt || !lt) && row_ok && in_row && x >= 1 && x <= w - 2) {
-                    word[j] |= 1u << (k0 + q);
-                    if (PREFILTER && ex_cheap_tests_pass(p1[j], p1[j + 1], p1[j + 2], c1[j], c1[j + 1], c1[j + 2], n1[j], n1[j + 1], n1[j + 2]))
-                        pass[j] |= 1u << (k0 + q);
-                }
+                if ((!gt || !lt) && row_ok && in_row && x >= 1 && x <= w - 2) word[j] |= 1u << (k0 + q);
             }
 #pragma unroll
             for (int j = 0; j < 5; ++j) { pmax[j] = cmax[j]; pmin[j] = cmin[j]; }
-            if (PREFILTER) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) { p1[j] = c1[j]; c1[j] = n1[j]; }
-            }
         }
     }
-    if (in_row) {
-        const size_t at = (size_t)b * mask_words_per_image + L.mask_off + (size_t)yw * w + x0;
+    if (!in_row) return;
+    const size_t at = (size_t)b * mask_words_per_image + L.mask_off + (size_t)yw * w + x0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (x0 + j < w) {
-                mask[at + j] = word[j];
-                if (PREFILTER) pass_mask[at + j] = pass[j];
+    for (int j = 0; j < 4; ++j) {
+        if (x0 + j >= w) break;
+        mask[at + j] = word[j];
+        if (PREFILTER) {
+            // the candidates (a few per cent of the pixels) fetch their 3x3 neighbourhood of the middle layer again: it has
+            // just streamed through this SM's L1, and keeping three rows of it in registers next to the scan above would
+            // double the kernel's register count for the sake of one pixel in twenty
+            const float* c1 = L.d1 + img + x0 + j;
+            uint32_t todo = word[j], pass = 0;
+            float nb[9];
+            auto fetch = [&](int k) {   // 1 <= y <= h - 2 and 1 <= x <= w - 2 for every candidate
+                const float* r = c1 + (size_t)(ybeg + k) * pitch;
+                nb[0] = __ldg(r - pitch - 1); nb[1] = __ldg(r - pitch); nb[2] = __ldg(r - pitch + 1);
+                nb[3] = __ldg(r - 1); nb[4] = __ldg(r); nb[5] = __ldg(r + 1);
+                nb[6] = __ldg(r + pitch - 1); nb[7] = __ldg(r + pitch); nb[8] = __ldg(r + pitch + 1);
+            };
+            int k = todo ? __ffs(todo) - 1 : 0;
+            if (todo) fetch(k);
+            while (todo) {   // the next candidate's loads are issued before this one's arithmetic
+                todo &= todo - 1;
+                const float c0 = nb[0], c1v = nb[1], c2 = nb[2], c3 = nb[3], c4 = nb[4], c5 = nb[5], c6 = nb[6], c7 = nb[7], c8 = nb[8];
+                const int kk = k;
+                if (todo) { k = __ffs(todo) - 1; fetch(k); }
+                if (ex_cheap_tests_pass(c0, c1v, c2, c3, c4, c5, c6, c7, c8)) pass |= 1u << kk;
             }
+            pass_mask[at + j] = pass;
+        }
     }
 }
 

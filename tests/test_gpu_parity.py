@@ -412,7 +412,7 @@ def test_cli_reads_jpeg_and_png_band0(built, parrot, tmp_path):
         if ext == "png":
             assert np.array_equal(band0, parrot)                       # lossless: band 0 is the R channel
         else:
-            assert np.abs(band0 - parrot).mean() < 2.0                   # lossy, but the same picture
+            assert np.abs(band0 - parrot).mean() < 4.0                   # lossy, but the same picture
         out = tmp_path / f"sift_{ext}.txt"
         p = subprocess.run([os.path.join(ROOT, "sift_b200", "sift"), str(f), "-r", "1", "--out", str(out)], capture_output=True, text=True)
         assert p.returncode == 0 and "interest points" in p.stdout, p.stderr
