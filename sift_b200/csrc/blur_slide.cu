@@ -628,7 +628,7 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 static int slide_partition(int strips, int batch, int h, int R, int nwarp, int n_sm, int cps, int* lanes, uint32_t* share, uint32_t* total) {
     static const int cps_cap = env_int("SIFT_GPU_SLIDE_CPS", 0);          // development knobs
     static const int even = env_int("SIFT_GPU_SLIDE_CPS_EVEN", 0);
-    static const int min_mult = env_int("SIFT_GPU_SLIDE_MIN_SHARE", 4);
+    static const int min_mult = env_int("SIFT_GPU_SLIDE_MIN_SHARE", 1);   // x (2R + 8) rows: a single image still spreads over the GPU (measured: 4 -> 1 takes a lone 1080p pyramid from 559 to 332 us, batches do not care)
     const uint64_t tot = (uint64_t)batch * (uint64_t)h;
     if (tot >= (1ull << 31) || strips < 1) return -1;
     if (cps_cap > 0 && cps > cps_cap) cps = cps_cap;

@@ -116,8 +116,9 @@ int launch_extrema(const ScanLayer* layers_dev, const ScanLayer* layers_host, in
                    uint32_t mask_words_per_image, uint32_t* mask, uint32_t* pass_mask, uint32_t* col_count, uint32_t* col_off,
                    Cand* cands, size_t cand_stride, uint32_t* n_cand, int batch, cudaStream_t s, uint64_t* launches);
 
+constexpr int kCompactSlices = 1024;   // most slices per image of the survivor compaction (slice_scratch: batch x kCompactSlices words)
 int launch_eliminate(const ScanLayer* layers_dev, int n_layers, Cand* cands, size_t cand_stride,
-                     const uint32_t* n_cand, Surv* survivors, size_t surv_stride, uint32_t* n_surv, int dogs_per_epoch,
+                     const uint32_t* n_cand, Surv* survivors, size_t surv_stride, uint32_t* n_surv, uint32_t* slice_scratch, int dogs_per_epoch,
                      int batch, cudaStream_t s, uint64_t* launches);
 
 // weight tables: blur(level, 1.6f) top-left 16x16 of every (image, target slot)

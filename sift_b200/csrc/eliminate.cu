@@ -3,10 +3,10 @@
 //   inverse(-H) fails -> reject; linearSolve(inv, grad) fails -> reject; any component > 127.5 ->
 //   reject; f = dot(grad, ext) * (0.5 + D(x,y)) [double], f < 7.65 -> reject; det < 0 -> reject;
 //   tr^2/det > 12.1f -> reject.  loc/scale are never moved.
-// One thread per candidate writes the verdict into the candidate list; a second kernel (one CTA per image, block-wide
-// prefix sums) then compacts the unfiltered candidates IN CANONICAL ORDER into the survivor list, each with its
-// position in the candidate vector (the host's std::sort replay works on those positions, and no longer has to sort
-// an atomically appended list back into order).
+// One thread per candidate writes the verdict into the candidate list; three small launches (count / offsets / write, see
+// below) then compact the unfiltered candidates IN CANONICAL ORDER into the survivor list, each with its position in the
+// candidate vector (the host's std::sort replay works on those positions, and no longer has to sort an atomically
+// appended list back into order).
 #include "common.cuh"
 #include "vigra_qr.cuh"
 
@@ -83,26 +83,82 @@ __global__ void __launch_bounds__(128) eliminate_kernel(const ScanLayer* __restr
     }
 }
 
-// Ordered compaction of the unfiltered candidates of image blockIdx.x.
-__global__ void __launch_bounds__(1024) compact_survivors_kernel(const Cand* __restrict__ cands, size_t cand_stride, const uint32_t* __restrict__ n_cand,
-                                                                 Surv* __restrict__ survivors, size_t surv_stride, uint32_t* __restrict__ n_surv) {
-    __shared__ uint32_t warp_sums[32];
+// Ordered compaction of the unfiltered candidates into the survivor list (canonical order), three small launches:
+//   count:   CTA (bx, image) counts the unfiltered candidates of its contiguous slice of the image's candidate list;
+//   offsets: one warp per image turns the slice counts into slice offsets and the survivor total;
+//   write:   every CTA writes its slice's survivors, in order, from its offset (block-wide prefix sums per round).
+// (The first version was one CTA per image walking the whole list: fine for a batch of 1080p frames, 2.5 ms for the 2.2 M
+// candidates of one 7680x4320 image.)
+constexpr int kCompactThreads = 256;
+constexpr int kCompactPer = 4;   // consecutive candidates per thread and round
+
+__device__ __forceinline__ void compact_slice(uint32_t n, uint32_t slices, uint32_t bx, uint32_t* lo, uint32_t* hi) {
+    const uint32_t round = kCompactThreads * kCompactPer;
+    const uint32_t chunk = ((n + slices - 1) / slices + round - 1) / round * round;
+    *lo = min(n, bx * chunk);
+    *hi = min(n, *lo + chunk);
+}
+
+__global__ void __launch_bounds__(kCompactThreads) survivors_count_kernel(const Cand* __restrict__ cands, size_t cand_stride,
+                                                                          const uint32_t* __restrict__ n_cand, uint32_t* __restrict__ slice_count) {
+    __shared__ uint32_t warp_sums[kCompactThreads / 32];
+    const int b = blockIdx.y;
+    uint32_t lo, hi;
+    compact_slice(n_cand[b], gridDim.x, blockIdx.x, &lo, &hi);
+    const Cand* cl = cands + (size_t)b * cand_stride;
+    uint32_t cnt = 0;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kCompactThreads) cnt += cl[i].filtered ? 0u : 1u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kCompactThreads / 32; ++w) t += warp_sums[w];
+        slice_count[(size_t)b * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(32) survivors_offsets_kernel(uint32_t* __restrict__ slice_count, uint32_t slices, uint32_t* __restrict__ n_surv) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    uint32_t* c = slice_count + (size_t)b * slices;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < slices; base += 32) {
+        const uint32_t v = base + lane < slices ? c[base + lane] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (base + lane < slices) c[base + lane] = carry + incl - v;   // exclusive
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) n_surv[b] = carry;
+}
+
+__global__ void __launch_bounds__(kCompactThreads) survivors_write_kernel(const Cand* __restrict__ cands, size_t cand_stride, const uint32_t* __restrict__ n_cand,
+                                                                          const uint32_t* __restrict__ slice_offset, Surv* __restrict__ survivors,
+                                                                          size_t surv_stride) {
+    __shared__ uint32_t warp_sums[kCompactThreads / 32];
     __shared__ uint32_t carry;
-    const int b = blockIdx.x;
-    const uint32_t n = n_cand[b];
+    const int b = blockIdx.y;
+    uint32_t lo, hi;
+    compact_slice(n_cand[b], gridDim.x, blockIdx.x, &lo, &hi);
+    if (lo >= hi) return;
     const Cand* cl = cands + (size_t)b * cand_stride;
     Surv* out = survivors + (size_t)b * surv_stride;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = slice_offset[(size_t)b * gridDim.x + blockIdx.x];
     __syncthreads();
-    constexpr int PER = 4;   // consecutive candidates per thread and round
-    for (uint32_t base = 0; base < n; base += 1024 * PER) {
+    constexpr int PER = kCompactPer;
+    for (uint32_t base = lo; base < hi; base += kCompactThreads * PER) {
         const uint32_t i0 = base + (uint32_t)threadIdx.x * PER;
         Cand c[PER];
         uint32_t cnt = 0;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            if (i0 + q < n) {
+            if (i0 + q < hi) {
                 c[q] = cl[i0 + q];
                 cnt += c[q].filtered ? 0u : 1u;
             } else {
@@ -118,13 +174,13 @@ __global__ void __launch_bounds__(1024) compact_survivors_kernel(const Cand* __r
         if (lane == 31) warp_sums[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            uint32_t ws = warp_sums[lane];
+            uint32_t ws = lane < kCompactThreads / 32 ? warp_sums[lane] : 0u;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
                 if (lane >= o) ws += t;
             }
-            warp_sums[lane] = ws;  // inclusive
+            if (lane < kCompactThreads / 32) warp_sums[lane] = ws;  // inclusive
         }
         __syncthreads();
         uint32_t slot = carry + (wid ? warp_sums[wid - 1] : 0u) + incl - cnt;
@@ -140,20 +196,25 @@ __global__ void __launch_bounds__(1024) compact_survivors_kernel(const Cand* __r
                 ++slot;
             }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = slot;
+        if (threadIdx.x == kCompactThreads - 1) carry = slot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) n_surv[b] = carry;
 }
 
 int launch_eliminate(const ScanLayer* layers_dev, int n_layers, Cand* cands, size_t cand_stride,
-                     const uint32_t* n_cand, Surv* survivors, size_t surv_stride, uint32_t* n_surv, int dogs_per_epoch,
+                     const uint32_t* n_cand, Surv* survivors, size_t surv_stride, uint32_t* n_surv, uint32_t* slice_scratch, int dogs_per_epoch,
                      int batch, cudaStream_t s, uint64_t* launches) {
     dim3 grid(148 * 4, batch);
     eliminate_kernel<<<grid, 128, 0, s>>>(layers_dev, n_layers, cands, cand_stride, n_cand, survivors, surv_stride, n_surv,
                                          dogs_per_epoch);
-    compact_survivors_kernel<<<batch, 1024, 0, s>>>(cands, cand_stride, n_cand, survivors, surv_stride, n_surv);
-    if (launches) *launches += 2;
+    // slices per image: enough CTAs to fill the device whatever the batch is, at most kCompactSlices (the scratch holds batch x that)
+    int slices = (148 * 8 + batch - 1) / batch;
+    slices = slices < 1 ? 1 : (slices > kCompactSlices ? kCompactSlices : slices);
+    dim3 gs(slices, batch);
+    survivors_count_kernel<<<gs, kCompactThreads, 0, s>>>(cands, cand_stride, n_cand, slice_scratch);
+    survivors_offsets_kernel<<<batch, 32, 0, s>>>(slice_scratch, (uint32_t)slices, n_surv);
+    survivors_write_kernel<<<gs, kCompactThreads, 0, s>>>(cands, cand_stride, n_cand, slice_scratch, survivors, surv_stride);
+    if (launches) *launches += 4;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -739,38 +739,63 @@ int launch_blur(const BlurArgs& a, int batch, bool fma, cudaStream_t s, uint64_t
 
 // ---------------------------------------------------------------------------------------------
 // resizeImageNoInterpolation: dst(x, y) = src(map_x[x], map_y[y]); the maps are produced on the host
-// by the literal accumulated-double walk.
-__global__ void resize_nn_kernel(const float* __restrict__ src, size_t src_stride, int src_pitch, float* __restrict__ dst,
-                                 size_t dst_stride, int dst_pitch, int dw, int dh, const int* __restrict__ map_x,
-                                 const int* __restrict__ map_y, int z0) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= dw || y >= dh) return;
+// by the literal accumulated-double walk.  A thread writes four adjacent destination pixels as one 16-byte store (row
+// pitches are multiples of 32 floats); its four gathered sources are neighbours in one row, i.e. L1 hits.
+__global__ void __launch_bounds__(256) resize_nn_kernel(const float* __restrict__ src, size_t src_stride, int src_pitch, float* __restrict__ dst,
+                                                        size_t dst_stride, int dst_pitch, int dw, int dh, const int* __restrict__ map_x,
+                                                        const int* __restrict__ map_y, int z0) {
+    const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (x >= dw) return;
     const int b = blockIdx.z + z0;
-    dst[(size_t)b * dst_stride + (size_t)y * dst_pitch + x] = src[(size_t)b * src_stride + (size_t)map_y[y] * src_pitch + map_x[x]];
+    int mx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mx[j] = map_x[x + j < dw ? x + j : dw - 1];
+    for (int y = blockIdx.y; y < dh; y += gridDim.y) {
+        const float* srow = src + (size_t)b * src_stride + (size_t)map_y[y] * src_pitch;
+        float4 v;
+        v.x = srow[mx[0]]; v.y = srow[mx[1]]; v.z = srow[mx[2]]; v.w = srow[mx[3]];
+        float* d = dst + (size_t)b * dst_stride + (size_t)y * dst_pitch + x;
+        if (x + 3 < dw) *reinterpret_cast<float4*>(d) = v;
+        else {
+            d[0] = v.x;
+            if (x + 1 < dw) d[1] = v.y;
+            if (x + 2 < dw) d[2] = v.z;
+        }
+    }
 }
 
 int launch_resize_nn(const float* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int dw,
                      int dh, const int* map_x, const int* map_y, int z0, int batch, cudaStream_t s, uint64_t* launches) {
-    dim3 grid((dw + 255) / 256, dh, batch);
+    dim3 grid((dw + 1023) / 1024, dh < 1024 ? dh : 1024, batch);
     resize_nn_kernel<<<grid, 256, 0, s>>>(src, src_stride, src_pitch, dst, dst_stride, dst_pitch, dw, dh, map_x, map_y, z0);
     if (launches) ++*launches;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, size_t src_stride, int src_pitch, float* __restrict__ dst,
-                                 size_t dst_stride, int dst_pitch, int w, int h) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+// importImage's widening of 8-bit pixels (main.cpp:52-54): four pixels per thread (one 4-byte load, one 16-byte store) where the
+// row start is aligned, single pixels otherwise.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, size_t src_stride, int src_pitch, float* __restrict__ dst,
+                                                        size_t dst_stride, int dst_pitch, int w, int h) {
+    const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int b = blockIdx.z;
     if (x >= w) return;
-    for (int y = blockIdx.y; y < h; y += gridDim.y)
-        dst[(size_t)b * dst_stride + (size_t)y * dst_pitch + x] = (float)src[(size_t)b * src_stride + (size_t)y * src_pitch + x];
+    const bool vec = (src_pitch & 3) == 0 && (src_stride & 3) == 0 && ((uintptr_t)src & 3) == 0 && x + 3 < w;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const uint8_t* sp = src + (size_t)b * src_stride + (size_t)y * src_pitch + x;
+        float* dp = dst + (size_t)b * dst_stride + (size_t)y * dst_pitch + x;
+        if (vec) {
+            const uchar4 u = *reinterpret_cast<const uchar4*>(sp);
+            *reinterpret_cast<float4*>(dp) = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+        } else {
+            for (int j = 0; j < 4 && x + j < w; ++j) dp[j] = (float)sp[j];
+        }
+    }
 }
 
 int launch_u8_to_f32(const uint8_t* src, size_t src_stride, int src_pitch, float* dst, size_t dst_stride, int dst_pitch, int w,
                      int h, int batch, cudaStream_t s, uint64_t* launches) {
-    dim3 grid((w + 255) / 256, h < 256 ? h : 256, batch);
+    dim3 grid((w + 1023) / 1024, h < 540 ? h : 540, batch);
     u8_to_f32_kernel<<<grid, 256, 0, s>>>(src, src_stride, src_pitch, dst, dst_stride, dst_pitch, w, h);
     if (launches) ++*launches;
     SIFT_CUDA_TRY(cudaGetLastError());

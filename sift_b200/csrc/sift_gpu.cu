@@ -226,6 +226,7 @@ struct Slot {
     Cand* d_cands = nullptr;
     Surv* d_surv = nullptr;
     uint32_t *d_n_cand = nullptr, *d_n_surv = nullptr;
+    uint32_t* d_slice = nullptr;   // survivor compaction scratch: B x kCompactSlices
     uint32_t *h_n_cand = nullptr, *h_n_surv = nullptr;  // pinned
     Surv* h_surv = nullptr;                              // pinned: B x kSurvFirst (speculative copy)
     std::vector<std::vector<Surv>> surv_overflow;        // per image, only when n_surv > kSurvFirst
@@ -545,6 +546,7 @@ static int alloc_buffers(sift_gpu_ctx* c) {
         CTX_CUDA(cudaMalloc(&S.d_surv, sizeof(Surv) * cand_cap * (size_t)B));
         CTX_CUDA(cudaMalloc(&S.d_n_cand, sizeof(uint32_t) * (size_t)B));
         CTX_CUDA(cudaMalloc(&S.d_n_surv, sizeof(uint32_t) * (size_t)B));
+        CTX_CUDA(cudaMalloc(&S.d_slice, sizeof(uint32_t) * (size_t)B * kCompactSlices));
         CTX_CUDA(cudaHostAlloc(&S.h_n_cand, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
         CTX_CUDA(cudaHostAlloc(&S.h_n_surv, sizeof(uint32_t) * (size_t)B, cudaHostAllocDefault));
         CTX_CUDA(cudaHostAlloc(&S.h_surv, sizeof(Surv) * (size_t)kSurvFirst * (size_t)B, cudaHostAllocDefault));
@@ -661,6 +663,7 @@ static int run_pyramid_group(sift_gpu_ctx* c, Slot& S, const Plan* p, const Plan
     if (c->prm.subpixel) {
         CTX_TRY(launch(blur_args(c, c->up_blur, S.d_in, c->max_in_px, p->in_pitch, S.d_up_tmp, c->max_in_px, p->in_pitch, nullptr, 0, 0,
                                  p->in_w, p->in_h, ps.has_up ? ps.map_up : nullptr)));
+        mark("resize x2", 0, p->ow[0], p->oh[0]);
         CTX_TRY(launch_resize_nn(S.d_up_tmp, c->max_in_px, p->in_pitch, S.d_up, c->maxP[0], p->pitch[0], p->ow[0], p->oh[0],
                                  p->d_maps + p->up_mx, p->d_maps + p->up_my, z0, cnt, s, L));
         base_src = S.d_up;
@@ -880,7 +883,7 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
                                    S.d_mask + c->mask_cap * (size_t)c->B, S.d_col_count, S.d_col_off, S.d_cands, c->cand_cap, S.d_n_cand, nb, s, L));
             CTX_CUDA(mark(3));
             CTX_TRY(launch_eliminate(ps.layers_dev, (int)ps.layers_host.size(), S.d_cands, c->cand_cap, S.d_n_cand, S.d_surv, c->cand_cap,
-                                     S.d_n_surv, c->D, nb, s, L));
+                                     S.d_n_surv, S.d_slice, c->D, nb, s, L));
             CTX_CUDA(mark(4));
             CTX_CUDA(cudaMemcpyAsync(S.h_n_cand, S.d_n_cand, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
             CTX_CUDA(cudaMemcpyAsync(S.h_n_surv, S.d_n_surv, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, s));
@@ -1259,7 +1262,7 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
         for (auto& kv : S.graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         S.graphs.clear();
         cudaFree(S.d_mask); cudaFree(S.d_col_count); cudaFree(S.d_col_off); cudaFree(S.d_cands); cudaFree(S.d_surv);
-        cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv);
+        cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFree(S.d_slice); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv);
         cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_key_first); cudaFree(S.d_orient); cudaFree(S.d_npeaks);
         cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_tables);
         cudaFreeHost(S.h_keys); cudaFreeHost(S.h_key_img); cudaFreeHost(S.h_key_first); cudaFreeHost(S.h_orient); cudaFreeHost(S.h_npeaks);
@@ -1577,7 +1580,7 @@ int sift_gpu_debug_eliminate(sift_gpu_ctx* c, const float* d0, const float* d1, 
         rc = SIFT_GPU_E_CUDA;
     if (!rc && n && cudaMemcpy(d_c, hc.data(), sizeof(Cand) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
     if (!rc && cudaMemcpy(S.n_cand, &n, sizeof n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
-    if (!rc) rc = launch_eliminate(S.dev, 1, d_c, 0, S.n_cand, d_s, std::max<uint32_t>(n, 1), d_ns, 3, 1, c->slots[0].stream, nullptr);
+    if (!rc) rc = launch_eliminate(S.dev, 1, d_c, 0, S.n_cand, d_s, std::max<uint32_t>(n, 1), d_ns, c->slots[0].d_slice, 3, 1, c->slots[0].stream, nullptr);
     if (!rc && cudaStreamSynchronize(c->slots[0].stream) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
     if (!rc && n && cudaMemcpy(hc.data(), d_c, sizeof(Cand) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SIFT_GPU_E_CUDA;
     cudaFree(d_c); cudaFree(d_s); cudaFree(d_ns);

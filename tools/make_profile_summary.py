@@ -48,18 +48,25 @@ def kernels(tag, rep, batch):
             ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
             ("launch__registers_per_thread", "regs"), ("launch__occupancy_limit_shared_mem", "CTAs/SM (smem)")]
     stalls = [h for h in hdr if "issue_stalled" in h and "per_issue_active" in h]
-    out = [f"# {tag}: ncu --set full, pyramid kernels (batch {batch})", ""]
+    out = [f"# {tag}: ncu --set full --clock-control none, one device pass of {batch} 1080p frames (exact blur arithmetic)", "",
+           "DRAM % is ncu's gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed (of the device's nominal peak, not of the measured copy bandwidth).", ""]
     total_dram = 0.0
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
         out.append(f"## `{name}` grid {r[idx['Grid Size']]}")
         for m, label in want:
             if m in idx:
-                out.append(f"* {label}: {r[idx[m]]}")
+                if m.startswith("dram__bytes"):
+                    mb = float(r[idx[m]].replace(",", "")) * scale.get(rows[1][idx[m]], 1e6) / 1e6
+                    out.append(f"* {label}: {mb:.1f}")
+                else:
+                    out.append(f"* {label}: {r[idx[m]]}")
         units = {h: rows[1][idx[h]] for h in ("dram__bytes_read.sum", "dram__bytes_write.sum") if h in idx}
         for h, u in units.items():
             v = float(r[idx[h]].replace(",", ""))
-            total_dram += v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1e6)
+            if "blur" in name or "resize" in name:   # the pyramid + DoG stage only
+                total_dram += v * scale.get(u, 1e6)
         ss = sorted(((float(r[idx[h]].replace(",", "") or 0), h) for h in stalls), reverse=True)[:5]
         out.append("* stalls per issued instruction: " + ", ".join(
             f"{h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} {v:.2f}" for v, h in ss))
@@ -76,7 +83,8 @@ if __name__ == "__main__":
     dram = kernels(tag, rep, batch)
     n_k = len([1 for _ in open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md")) if _.startswith("## ")])
     json.dump({"dram_bytes_per_image": dram / batch, "kernels_captured": n_k, "batch": batch,
-               "note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the captured pyramid kernels of one device pass / batch"},
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the captured blur / resize kernels (the pyramid + DoG stage) of one device pass / batch; "
+                       "levels below 200 rows (octaves 3-4, 1.3 % of the bytes) run as strip kernels that the capture's launch limit left out"},
               open(os.path.join(ROOT, "profiles", "pyramid_traffic.json"), "w"), indent=1)
     if len(sys.argv) > 4 and os.path.exists(sys.argv[4]):
         d = json.load(open(sys.argv[4]))
