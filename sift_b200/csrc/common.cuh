@@ -126,10 +126,12 @@ int launch_weight_tables(const LevelRef* targets_dev, int n_targets, const float
                          bool fma, int batch, cudaStream_t s, uint64_t* launches);
 // keys of all images concatenated; key_img[i] = image of key i; key_first[b] = first key of image b
 int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* keys, const uint32_t* key_img,
-                       uint32_t n_keys, float* orientation, uint32_t* n_peaks, float* peaks, cudaStream_t s,
+                       uint32_t n_keys, float* orientation, uint32_t* n_peaks, float* peaks, float2* grad_cache, cudaStream_t s,
                        uint64_t* launches);
 int launch_descriptors(const LevelRef* targets_dev, int n_targets, const float* tables, const KeyIn* keys,
                        const uint32_t* key_img, const uint32_t* key_first, uint32_t n_keys, const float* orientation,
-                       float* desc, cudaStream_t s, uint64_t* launches);
+                       float* desc, const float2* grad_cache, cudaStream_t s, uint64_t* launches);
+// grad_cache: n_keys x 256 (magnitude, orientation) pairs, written by launch_orientation and read by launch_descriptors when
+// both run over the same key list; null = the descriptor kernel computes the gradients itself
 
 }  // namespace siftgpu

@@ -103,7 +103,7 @@ constexpr int kHistPitch = 37;  // odd pitch: phase 2's column walk over 32 hist
 __global__ void __launch_bounds__(kOriThreads) orientation_kernel(const LevelRef* __restrict__ targets, const KeyIn* __restrict__ keys,
                                                                const uint32_t* __restrict__ key_img, uint32_t n_keys,
                                                                float* __restrict__ orientation, uint32_t* __restrict__ n_peaks,
-                                                               float* __restrict__ peaks) {
+                                                               float* __restrict__ peaks, float2* __restrict__ grad_cache) {
     __shared__ __align__(16) float s_val[4][kWin * kWin];
     __shared__ uint16_t s_bin[4][kWin * kWin];
     __shared__ float s_hist[kOriKeys][kHistPitch];
@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(kOriThreads) orientation_kernel(const LevelRef
                 const int wx = s >> 4, wy = s & 15;
                 float mag, ori;
                 gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &mag, &ori);
+                // the descriptor kernel needs the same 256 (magnitude, orientation) pairs of this window: the double sqrt and the
+                // atan2f are half of its instructions, 2 KB per keypoint through L2 / HBM is cheaper
+                if (grad_cache) grad_cache[(size_t)k * (kWin * kWin) + s] = make_float2(mag, ori);
                 const float g = G[(size_t)(y0 + wy) * T.pitch + x0 + wx];
                 s_val[wib][s] = mag * g;
                 uint16_t bi = (uint16_t)(int)floorf(ori / 10);
@@ -225,7 +228,8 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
                                                          const float* __restrict__ tables, const KeyIn* __restrict__ keys,
                                                          const uint32_t* __restrict__ key_img,
                                                          const uint32_t* __restrict__ key_first, uint32_t n_keys,
-                                                         const float* __restrict__ orientation, float* __restrict__ desc) {
+                                                         const float* __restrict__ orientation, float* __restrict__ desc,
+                                                         const float2* __restrict__ grad_cache) {
     __shared__ float s_val[4][kWin * kWin];
     __shared__ uint16_t s_bin[4][kWin * kWin];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -243,7 +247,12 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int s = lane + 32 * j, wx = s >> 4, wy = s & 15;
-            gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &M[j], &O[j]);
+            if (grad_cache) {   // written by the orientation kernel for this very key list
+                const float2 mo = grad_cache[(size_t)k * (kWin * kWin) + s];
+                M[j] = mo.x; O[j] = mo.y;
+            } else {
+                gradient_at(G, T.pitch, T.w, T.h, x0 + wx, y0 + wy, &M[j], &O[j]);
+            }
         }
         // replay earlier keypoints of this image and level whose window overlaps, in vector order
         const uint32_t first = key_first[img];
@@ -335,13 +344,13 @@ int launch_weight_tables(const LevelRef* targets_dev, int n_targets, const float
 }
 
 int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* keys, const uint32_t* key_img,
-                       uint32_t n_keys, float* orientation, uint32_t* n_peaks, float* peaks, cudaStream_t s,
+                       uint32_t n_keys, float* orientation, uint32_t* n_peaks, float* peaks, float2* grad_cache, cudaStream_t s,
                        uint64_t* launches) {
     (void)n_targets;
     if (n_keys == 0) return 0;
     const unsigned blocks = (unsigned)((n_keys + kOriKeys - 1) / kOriKeys);
     orientation_kernel<<<blocks < 148u * 8u ? blocks : 148u * 8u, kOriThreads, 0, s>>>(targets_dev, keys, key_img, n_keys, orientation,
-                                                                                n_peaks, peaks);
+                                                                                n_peaks, peaks, grad_cache);
     if (launches) ++*launches;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -349,11 +358,11 @@ int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* 
 
 int launch_descriptors(const LevelRef* targets_dev, int n_targets, const float* tables, const KeyIn* keys,
                        const uint32_t* key_img, const uint32_t* key_first, uint32_t n_keys, const float* orientation,
-                       float* desc, cudaStream_t s, uint64_t* launches) {
+                       float* desc, const float2* grad_cache, cudaStream_t s, uint64_t* launches) {
     if (n_keys == 0) return 0;
     const unsigned blocks = (unsigned)((n_keys + 3) / 4);
     descriptor_kernel<<<blocks < 148u * 8u ? blocks : 148u * 8u, 128, 0, s>>>(targets_dev, n_targets, tables, keys, key_img,
-                                                                               key_first, n_keys, orientation, desc);
+                                                                               key_first, n_keys, orientation, desc, grad_cache);
     if (launches) ++*launches;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;

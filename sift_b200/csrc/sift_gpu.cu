@@ -239,6 +239,7 @@ struct Slot {
     uint32_t* d_npeaks = nullptr; uint32_t* h_npeaks = nullptr;
     float* d_peaks = nullptr;
     float* d_desc = nullptr;
+    float2* d_grad = nullptr;     // per key: the 256 (magnitude, orientation) pairs of its window (orientation kernel -> descriptor kernel)
     float* d_tables = nullptr;
     size_t tables_cap = 0;
     // state of the pass in flight
@@ -562,7 +563,7 @@ static int alloc_buffers(sift_gpu_ctx* c) {
 static int ensure_key_capacity(sift_gpu_ctx* c, Slot& S, size_t n) {
     if (n <= S.key_cap) return 0;
     size_t cap = std::max<size_t>(n * 3 / 2, 4096);
-    cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_orient); cudaFree(S.d_npeaks); cudaFree(S.d_peaks); cudaFree(S.d_desc);
+    cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_orient); cudaFree(S.d_npeaks); cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_grad);
     cudaFreeHost(S.h_keys); cudaFreeHost(S.h_key_img); cudaFreeHost(S.h_orient); cudaFreeHost(S.h_npeaks);
     S.key_cap = 0;
     CTX_CUDA(cudaMalloc(&S.d_keys, sizeof(KeyIn) * cap));
@@ -571,6 +572,7 @@ static int ensure_key_capacity(sift_gpu_ctx* c, Slot& S, size_t n) {
     CTX_CUDA(cudaMalloc(&S.d_npeaks, sizeof(uint32_t) * cap));
     CTX_CUDA(cudaMalloc(&S.d_peaks, sizeof(float) * 36 * cap));
     CTX_CUDA(cudaMalloc(&S.d_desc, sizeof(float) * kDescLen * cap));
+    CTX_CUDA(cudaMalloc(&S.d_grad, sizeof(float2) * 256 * cap));
     CTX_CUDA(cudaHostAlloc(&S.h_keys, sizeof(KeyIn) * cap, cudaHostAllocDefault));
     CTX_CUDA(cudaHostAlloc(&S.h_key_img, sizeof(uint32_t) * cap, cudaHostAllocDefault));
     CTX_CUDA(cudaHostAlloc(&S.h_orient, sizeof(float) * cap, cudaHostAllocDefault));
@@ -1000,13 +1002,13 @@ static int end_replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_ind
             CTX_CUDA(cudaMalloc(&S.d_tables, sizeof(float) * tables_need));
             S.tables_cap = tables_need;
         }
-        CTX_TRY(launch_orientation(ps.targets_dev, n_targets, S.d_keys, S.d_key_img, (uint32_t)n_keys, S.d_orient, S.d_npeaks, S.d_peaks, s, L));
+        CTX_TRY(launch_orientation(ps.targets_dev, n_targets, S.d_keys, S.d_key_img, (uint32_t)n_keys, S.d_orient, S.d_npeaks, S.d_peaks, S.d_grad, s, L));
     }
     CTX_CUDA(cudaEventRecord(S.ev[8], s));
     if (n_keys) {
         CTX_TRY(launch_weight_tables(ps.targets_dev, n_targets, c->d_taps + c->w16_blur.tap_off, c->w16_blur.r, S.d_tables, c->fma, nb, s, L));
         CTX_TRY(launch_descriptors(ps.targets_dev, n_targets, S.d_tables, S.d_keys, S.d_key_img, S.d_key_first, (uint32_t)n_keys, S.d_orient,
-                                   S.d_desc, s, L));
+                                   S.d_desc, S.d_grad, s, L));
     }
     CTX_CUDA(cudaEventRecord(S.ev[9], s));
     if (n_keys) {
@@ -1108,7 +1110,7 @@ static int redo_with_extra_orientations(sift_gpu_ctx* c, Slot& S, int slot_index
         CTX_CUDA(cudaMemcpyAsync(S.d_key_first, S.h_key_first, sizeof(uint32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, s));
         CTX_CUDA(cudaMemcpyAsync(S.d_orient, S.h_orient, sizeof(float) * n_keys, cudaMemcpyHostToDevice, s));
         CTX_TRY(launch_descriptors(ps.targets_dev, (int)ps.targets_host.size(), S.d_tables, S.d_keys, S.d_key_img, S.d_key_first, (uint32_t)n_keys,
-                                   S.d_orient, S.d_desc, s, &S.launches));
+                                   S.d_orient, S.d_desc, nullptr /* another key list: recompute the gradients */, s, &S.launches));
         CTX_CUDA(cudaMemcpyAsync(S.h_desc, S.d_desc, sizeof(float) * kDescLen * n_keys, cudaMemcpyDeviceToHost, s));
     }
     CTX_CUDA(cudaStreamSynchronize(s));
@@ -1264,7 +1266,7 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
         cudaFree(S.d_mask); cudaFree(S.d_col_count); cudaFree(S.d_col_off); cudaFree(S.d_cands); cudaFree(S.d_surv);
         cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFree(S.d_slice); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv);
         cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_key_first); cudaFree(S.d_orient); cudaFree(S.d_npeaks);
-        cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_tables);
+        cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_grad); cudaFree(S.d_tables);
         cudaFreeHost(S.h_keys); cudaFreeHost(S.h_key_img); cudaFreeHost(S.h_key_first); cudaFreeHost(S.h_orient); cudaFreeHost(S.h_npeaks);
         for (auto& e : S.ev) if (e) cudaEventDestroy(e);
         for (auto& e : S.ev_join) if (e) cudaEventDestroy(e);
