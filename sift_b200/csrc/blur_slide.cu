@@ -70,6 +70,23 @@ constexpr int slide_min_blocks() {
     return by_smem < cap ? by_smem : cap;
 }
 
+// Resident CTAs per SM each kernel is compiled for (__launch_bounds__ minimum): 1 = leave the register count to ptxas.  The
+// values were picked from in-situ launch times (tools/build_variant.sh builds the alternatives).
+#ifndef SL_MINB_R5
+#define SL_MINB_R5 1
+#endif
+#ifndef SL_MINB_R7
+#define SL_MINB_R7 1
+#endif
+#ifndef SL_MINB_R10
+#define SL_MINB_R10 1
+#endif
+#ifndef SL_MINB_R14
+#define SL_MINB_R14 1
+#endif
+template <int R>
+constexpr int slide_min_blocks() { return R == 5 ? SL_MINB_R5 : R == 7 ? SL_MINB_R7 : R == 10 ? SL_MINB_R10 : R == 14 ? SL_MINB_R14 : 1; }
+
 template <int R>
 struct SlideTaps {        // tk[j] = tap applied to source index x - R + j; symmetric (tk[j] == tk[2R - j], checked on the host)
     float tk[R + 1];      // j <= R; the column pass uses them as (tk, tk): ptxas folds that into a scalar-broadcast FFMA2 operand
@@ -266,7 +283,7 @@ __device__ __forceinline__ void sl_col_chunk(float2 (&acc)[2 * R], const float* 
 }
 
 template <int R, bool FMA, int MODE>
-__global__ void __launch_bounds__(64) blur_slide_kernel(const __grid_constant__ CUtensorMap map8, const __grid_constant__ CUtensorMap map1,
+__global__ void __launch_bounds__(64, slide_min_blocks<R>()) blur_slide_kernel(const __grid_constant__ CUtensorMap map8, const __grid_constant__ CUtensorMap map1,
                                                         const SlideArgs sa, const SlideTaps<R> taps) {
     constexpr bool DOG = MODE != 0;
     using C = SL<R, DOG>;
