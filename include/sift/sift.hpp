@@ -38,7 +38,7 @@ class Sift {
     // --- extensions ---
     std::vector<std::vector<InterestPoint>> calculateBatch(std::vector<Image>& imgs);
     void setDevice(int device) { device_ = device; }
-    void setFlags(unsigned flags) { flags_ = flags; }  // SIFT_GPU_FLAG_*; takes effect at the next context creation
+    void setFlags(unsigned flags) { flags_ = flags; }  // SIFT_GPU_FLAG_* (default: STRICT); takes effect at the next context creation
     void setMaxBatch(int n) { max_batch_ = n; }
 
    private:
@@ -50,7 +50,7 @@ class Sift {
     sift_gpu_ctx* ctx_ = nullptr;
     std::ptrdiff_t ctx_w_ = 0, ctx_h_ = 0;
     int ctx_batch_ = 0, device_ = 0, max_batch_ = 1;
-    unsigned flags_ = 0;
+    unsigned flags_ = 0x2u;  // SIFT_GPU_FLAG_STRICT: like the reference, calculate() throws where the dead 16x16 blur of sift.cpp:184 would (octaves >= 6)
 };
 
 // main.cpp:78-89: header line, then "[x, y]\tscale\torientation\t[d0, d1, ..., ]" per point with default

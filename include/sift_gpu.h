@@ -34,7 +34,9 @@ extern "C" {
                                               replaying the reference's std::sort permutation (sift.cpp:37,49).
                                               Same keypoint set; descriptors of overlapping windows differ. */
 #define SIFT_GPU_FLAG_STRICT 0x2u          /* reproduce the reference's exception from the dead 16x16 blur
-                                              (sift.cpp:184) as SIFT_GPU_E_PRECONDITION */
+                                              (sift.cpp:184) as SIFT_GPU_E_PRECONDITION.  NOT the default of the C ABI:
+                                              without it a run with >= 6 octaves returns keypoints where the reference
+                                              aborts.  sift::Sift (include/sift/sift.hpp) sets it by default. */
 #define SIFT_GPU_FLAG_FMA_BLUR 0x4u        /* fused multiply-add in the Gaussian blur (faster; DoG within 1e-4 relative
                                               of the reference instead of bit-identical to its mulss/addss order) */
 #define SIFT_GPU_FLAG_KEEP_UPSAMPLED 0x8u  /* subpixel: copy the 2x image back (reference overwrites img, sift.cpp:21) */
@@ -82,7 +84,8 @@ typedef struct sift_gpu_keypoint {
     uint16_t reserved;
 } sift_gpu_keypoint;
 
-/* Result of one image.  Buffers are ctx-owned pinned host memory, valid until the next run/destroy. */
+/* Result of one image.  Buffers are ctx-owned host memory (desc: pinned, filled straight from the device; kps: ordinary
+ * heap memory assembled on the host), valid until the next run/destroy. */
 typedef struct sift_gpu_result {
     int32_t status;              /* per-image SIFT_GPU_* code */
     uint32_t n;                  /* keypoints returned, in the reference's vector order */

@@ -9,10 +9,21 @@
 //
 // Key: 0 = unfiltered (sorts first), 1 = filtered.  comp(a, b) == (a == 0 && b == 1).
 // tests/test_abi_cpu.py compares the result with the real std::sort over many sizes and densities.
+//
+// Which std::sort: the dense hand-off below calls libstdc++'s own std::__introsort_loop, an internal whose signature has
+// been stable from GCC 4.9 to 15 (checked range below); outside that range, or on another standard library, every segment
+// takes the sparse simulation, which implements the same algorithm (libstdc++'s: median of first+1 / mid / last-1 moved to
+// first, unguarded Hoare partition, 16-element threshold, depth limit 2*lg n) and gives the same permutation, only slower.
+// The order contract is therefore "GNU libstdc++'s introsort" — the library the reference's shipped binary (GCC 7.1) and
+// this build (GCC 13) both use.
 #pragma once
 #include <algorithm>
 #include <cstdint>
 #include <vector>
+
+#if defined(__GLIBCXX__) && defined(_GLIBCXX_RELEASE) && _GLIBCXX_RELEASE >= 5 && _GLIBCXX_RELEASE <= 15
+#define SIFT_ORDER_REPLAY_LIBSTDCXX 1
+#endif
 
 namespace siftgpu {
 
@@ -55,7 +66,7 @@ class SparseFilterSort {
                 heap_fallback(f, l, za, zb);
                 return;
             }
-#ifdef __GLIBCXX__
+#ifdef SIFT_ORDER_REPLAY_LIBSTDCXX
             if ((zb - za) * 2 >= (size_t)(l - f)) {  // half unfiltered: cheaper to let libstdc++ run on the real thing
                 dense_segment(f, l, depth, za, zb);
                 return;
@@ -82,7 +93,7 @@ class SparseFilterSort {
         }
     }
 
-#ifdef __GLIBCXX__
+#ifdef SIFT_ORDER_REPLAY_LIBSTDCXX
     // A segment in which at least half of the elements is unfiltered is materialised as (filtered bit | id) words and
     // handed to libstdc++'s own __introsort_loop with the depth budget it has left at this point of the recursion — the
     // same code std::sort would be running here, so the permutation is the reference's by construction.

@@ -90,8 +90,10 @@ class Pool {
         held_n = n;
         if (n <= 0 || workers.empty()) return;
         {
+            // total and pending first, the item counter last: a worker still in the item loop of the previous job that draws
+            // an index after the reset must already see this job's bounds
             std::lock_guard<std::mutex> g(m);
-            job = &held; next = 0; total = n; pending = n;
+            job = &held; total.store(n); pending.store(n); next.store(0);
         }
         cv.notify_all();
     }
@@ -121,13 +123,13 @@ class Pool {
             const std::function<void(int)>* j;
             {
                 std::unique_lock<std::mutex> lk(m);
-                cv.wait(lk, [this] { return stop || (job && next.load() < total); });
+                cv.wait(lk, [this] { return stop || (job && next.load() < total.load()); });
                 if (stop) return;
                 j = job;
             }
             for (;;) {
                 int i = next.fetch_add(1);
-                if (i >= total) break;
+                if (i >= total.load()) break;
                 (*j)(i);
                 if (pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m); done_cv.notify_all(); }
             }
@@ -139,8 +141,7 @@ class Pool {
     const std::function<void(int)>* job = nullptr;
     std::function<void(int)> held;
     int held_n = 0;
-    std::atomic<int> next{0}, pending{0};
-    int total = 0;
+    std::atomic<int> next{0}, pending{0}, total{0};
     bool stop = false;
 };
 
@@ -1295,6 +1296,24 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
     c->outs.clear();
     c->outs.resize((size_t)n_images);
     int first_error = SIFT_GPU_OK;
+    // Whatever way this call is left — a CUDA error in the middle of the pipelined loop included — no replay job may keep
+    // running on the worker pool and no slot may keep device work queued on buffers the next call reuses.
+    struct Quiesce {
+        sift_gpu_ctx* c;
+        bool clean = false;
+        ~Quiesce() {
+            if (clean) return;
+            if (c->pool) c->pool->end();
+            for (int si = 0; si < c->n_slots; ++si) {
+                Slot& S = c->slots[si];
+                if (S.stream) cudaStreamSynchronize(S.stream);
+                for (cudaStream_t a : S.aux)
+                    if (a) cudaStreamSynchronize(a);
+                S.busy = false;
+            }
+            cudaGetLastError();
+        }
+    } quiesce{c};
     // split the images into device passes: runs of equal shape and dtype, at most max_batch each
     std::vector<PassPlan> passes;
     int i = 0;
@@ -1403,6 +1422,7 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
                 g_rep_ns[4] * 1e-3 / std::max(1, n_images));
     for (auto& v : g_rep_ns) v = 0;
     for (double& v : g_trace) v = 0.0;
+    quiesce.clean = true;
     return first_error;
 }
 
