@@ -718,6 +718,10 @@ static int launch_slide_r(const BlurArgs& a, int batch, bool fma, int idx, cudaS
     const SlideDevInfo& d = g_slide_dev[dev < 64 && dev >= 0 ? dev : 0];
     const int mode = a.dog ? (a.dst ? 1 : 2) : 0;
     if (!a.dog && !a.dst) return -1;
+    // SIFT_GPU_FLAG_FMA_BLUR permits fusing, it does not demand it: the r = 7 blur + DoG launch of a large level is bound by
+    // its memory access pattern, and there the exact-arithmetic instantiation (120 registers, no spills) is the faster one
+    // (324 vs 345 us for 64 1080p frames, measured on every build variant) — and it is bit-exact on top.
+    if (R == 7 && mode == 1 && (size_t)a.w * (size_t)a.h >= (1u << 20)) fma = false;
     if (mode == 1 && a.dst_pitch != a.dog_pitch) return -1;   // one row pointer serves both outputs
     // taps for radius R: tk[j], j = 0..2R, zero outside the real radius; the kernel relies on their symmetry
     const int r = a.r, pad = R - r;
@@ -735,6 +739,9 @@ static int launch_slide_r(const BlurArgs& a, int batch, bool fma, int idx, cudaS
     SlideArgs sa;
     sa.a = a;
     const int strips = (a.w + C::WC - 1) / C::WC;
+    // (Measured and not adopted: capping the resident CTAs of single launches.  In isolation blur + DoG r = 5 is 15 % faster at
+    // 4 CTAs/SM than at 9 and the fused r = 10 launch 7 % at 6, but with the image groups of a pass running side by side the
+    // caps cost 1-3 % of the stage.)
     const int cps = d.cps[idx][fma ? 1 : 0][mode];
     sa.strips = strips;
     const int ctas = slide_partition(strips, batch, a.h, R, C::NWARP, d.n_sm, cps, &sa.lanes, &sa.share, &sa.total);
