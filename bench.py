@@ -187,13 +187,16 @@ def measure_configs(device, flags, literal_cpu=True):
         pass
     k = capi.SQRT2_F32
     parrot = np.load(os.path.join(ROOT, "tests", "golden", "parrot_r.npy")).astype(np.float32)
-    cases = [("config1_parrot_488x600", parrot, 4, False),
-             ("config2_600x600_subpixel", synth_frame(600, 600, 0), 4, True),
-             ("config4_3840x2160_subpixel_6oct", synth_frame(3840, 2160, 0), 6, True)]
+    cases = [("config1_parrot_488x600", parrot, 4, False, DPE, 1.6, k),
+             ("config2_600x600_subpixel", synth_frame(600, 600, 0), 4, True, DPE, 1.6, k),
+             ("config4_3840x2160_subpixel_6oct", synth_frame(3840, 2160, 0), 6, True, DPE, 1.6, k),
+             # a schedule off the defaults (4 DoGs per octave, sigma 2.0, k 1.3: radii 6, 8, 10, 13, 17, ... instead of 5, 7, 10, 14, 19):
+             # every level still runs on the sliding kernel (next instantiated radius up, zero taps added)
+             ("nondefault_1080p_dpe4_sigma2.0_k1.3", synth_frame(1920, 1080, 0), 4, False, 4, 2.0, 1.3)]
     out = {}
-    for name, img, octaves, sub in cases:
+    for name, img, octaves, sub, dpe, sigma, kk in cases:
         h, w = img.shape
-        g = capi.SiftGpu(DPE, octaves, 1.6, k, sub, max_width=w, max_height=h, max_batch=1, device=device, flags=flags | capi.FLAG_SERIAL)
+        g = capi.SiftGpu(dpe, octaves, sigma, kk, sub, max_width=w, max_height=h, max_batch=1, device=device, flags=flags | capi.FLAG_SERIAL)
         lat, pyr, n = [], [], 0
         for i in range(7):
             t0 = time.perf_counter()
@@ -203,10 +206,10 @@ def measure_configs(device, flags, literal_cpu=True):
             n = int(r["kps"].size)
         g.close()
         lat, pyr = sorted(lat[2:]), sorted(pyr[2:])
-        pb = pyramid_bytes(w, h, octaves, DPE, sub)
+        pb = pyramid_bytes(w, h, octaves, dpe, sub)
         out[name] = {"gpu_latency_ms": lat[len(lat) // 2], "pyramid_ms": pyr[len(pyr) // 2], "pyramid_algorithmic_bytes": pb,
                      "pyramid_gbs": pb / (pyr[len(pyr) // 2] * 1e-3) / 1e9, "pyramid_frac_of_hbm_peak": pb / (pyr[len(pyr) // 2] * 1e-3) / 1e9 / peak,
-                     "keypoints": n, "octaves": octaves, "subpixel": sub}
+                     "keypoints": n, "octaves": octaves, "subpixel": sub, "dogs_per_octave": dpe, "sigma": sigma, "k": float(kk)}
     if literal_cpu and ol.ref_available(fast=False):
         L = ol.ref_lib(fast=False)
         for name, img, octaves, readme in (("literal_cpu_300x300", synth_frame(300, 300, 0), 4, "~0.7 s"),

@@ -66,12 +66,10 @@ class SparseFilterSort {
                 heap_fallback(f, l, za, zb);
                 return;
             }
-#ifdef SIFT_ORDER_REPLAY_LIBSTDCXX
             if ((zb - za) * 2 >= (size_t)(l - f)) {  // half unfiltered: cheaper to let libstdc++ run on the real thing
                 dense_segment(f, l, depth, za, zb);
                 return;
             }
-#endif
             --depth;
             const int64_t cut = partition_pivot(f, l, za, zb);
             const size_t zc = (size_t)(std::lower_bound(zp_.begin() + (long)za, zp_.begin() + (long)zb, (uint32_t)cut) - zp_.begin());
@@ -93,22 +91,71 @@ class SparseFilterSort {
         }
     }
 
-#ifdef SIFT_ORDER_REPLAY_LIBSTDCXX
-    // A segment in which at least half of the elements is unfiltered is materialised as (filtered bit | id) words and
-    // handed to libstdc++'s own __introsort_loop with the depth budget it has left at this point of the recursion — the
-    // same code std::sort would be running here, so the permutation is the reference's by construction.
+    // A segment in which at least half of the elements is unfiltered is materialised as (filtered bit | id) words and sorted
+    // for real.  With libstdc++ (checked release range above) by its own std::__introsort_loop with the depth budget left at
+    // this point of the recursion — the same code std::sort would be running here; elsewhere by the restatement below
+    // (SIFT_ORDER_REPLAY_OWN_DENSE selects it explicitly; tests compare both with std::sort).
     void dense_segment(int64_t f, int64_t l, int depth, size_t za, size_t zb) {
         seg_.assign((size_t)(l - f), 0x80000000u);
         for (size_t i = za; i < zb; ++i) seg_[(size_t)((int64_t)zp_[i] - f)] = id_[i];
+#if defined(SIFT_ORDER_REPLAY_LIBSTDCXX) && !defined(SIFT_ORDER_REPLAY_OWN_DENSE)
         auto comp = [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); };
         std::__introsort_loop(seg_.begin(), seg_.end(), (long)depth, __gnu_cxx::__ops::__iter_comp_iter(comp));
+#else
+        dense_introsort(seg_.data(), seg_.data() + seg_.size(), depth);
+#endif
         size_t z = za;
         for (int64_t p = f; p < l; ++p) {
             const uint32_t v = seg_[(size_t)(p - f)];
             if (!(v >> 31)) { zp_[z] = (uint32_t)p; id_[z] = v; ++z; }
         }
     }
-#endif
+
+    // libstdc++'s __introsort_loop for this comparator (key = bit 31; comp(a, b) = key(a) < key(b)), written out:
+    // __move_median_to_first(first, first + 1, mid, last - 1), __unguarded_partition(first + 1, last, first), recursion on the
+    // right part, iteration on the left, 16-element threshold, heap sort when the depth budget is used up.
+    static void dense_introsort(uint32_t* first, uint32_t* last, int depth) {
+        while (last - first > 16) {
+            if (depth == 0) {
+                std::partial_sort(first, last, last, [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
+                return;
+            }
+            --depth;
+            uint32_t* mid = first + (last - first) / 2;
+            {
+                uint32_t *a = first + 1, *b = mid, *c = last - 1;
+                const uint32_t ka = *a >> 31, kb = *b >> 31, kc = *c >> 31;
+                uint32_t* pick;
+                if (ka < kb) pick = (kb < kc) ? b : ((ka < kc) ? c : a);
+                else if (ka < kc) pick = a;
+                else if (kb < kc) pick = c;
+                else pick = b;
+                std::swap(*first, *pick);
+            }
+            uint32_t *lo = first + 1, *hi = last;
+            if (*first >> 31) {
+                // pivot filtered: `lo` runs over unfiltered elements and stops at every filtered one, `hi` steps down by one
+                for (;;) {
+                    while (!(*lo >> 31)) ++lo;
+                    --hi;
+                    if (!(lo < hi)) break;
+                    std::swap(*lo, *hi);
+                    ++lo;
+                }
+            } else {
+                // pivot unfiltered: `lo` never skips, `hi` skips filtered elements
+                for (;;) {
+                    --hi;
+                    while (*hi >> 31) --hi;
+                    if (!(lo < hi)) break;
+                    std::swap(*lo, *hi);
+                    ++lo;
+                }
+            }
+            dense_introsort(lo, last, depth);
+            last = lo;
+        }
+    }
 
     // contents of positions p and q trade places (p < q); keeps zp_[za, zb) sorted
     void swap_positions(int64_t p, int64_t q, size_t za, size_t zb) {
