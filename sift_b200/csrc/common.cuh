@@ -128,9 +128,20 @@ int launch_weight_tables(const LevelRef* targets_dev, int n_targets, const float
 int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* keys, const uint32_t* key_img,
                        uint32_t n_keys, float* orientation, uint32_t* n_peaks, float* peaks, float2* grad_cache, cudaStream_t s,
                        uint64_t* launches);
+// Spatial index of a pass's keys for the descriptor kernel: cells of 16 x 16 pixels per (image, target level); a key's
+// overlapping predecessors can only sit in its own cell and the eight around it.  Scratch owned by the caller:
+// count / offset / cursor: images * cells_per_image words each, cell_keys: one word per key.
+struct KeyGrid {
+    uint32_t* count;
+    uint32_t* offset;
+    uint32_t* cursor;
+    uint32_t* cell_keys;
+    int cw, ch;                 // cells per row / column of one target level
+    uint32_t cells_per_image;   // n_targets * cw * ch
+};
 int launch_descriptors(const LevelRef* targets_dev, int n_targets, const float* tables, const KeyIn* keys,
                        const uint32_t* key_img, const uint32_t* key_first, uint32_t n_keys, const float* orientation,
-                       float* desc, const float2* grad_cache, cudaStream_t s, uint64_t* launches);
+                       float* desc, const float2* grad_cache, const KeyGrid* grid, int batch, cudaStream_t s, uint64_t* launches);
 // grad_cache: n_keys x 256 (magnitude, orientation) pairs, written by launch_orientation and read by launch_descriptors when
 // both run over the same key list; null = the descriptor kernel computes the gradients itself
 

@@ -12,6 +12,8 @@
 //   accumulated contributions of every earlier keypoint whose window overlaps its own.  Each warp
 //   replays, in vector order, the earlier keypoints of the same level that overlap its window, then
 //   its own contribution, bins with (u16)floorf(o/45) % 7 and L1-normalises each 4x4 cell.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "vigra_qr.cuh"
 
@@ -224,14 +226,75 @@ __global__ void __launch_bounds__(256) weight_table_kernel(const LevelRef* __res
     }
 }
 
+constexpr int kMaxGridHits = 256;   // overlapping predecessors a warp sorts in shared memory; more than that: full scan
+
+// ---- key grid (KeyGrid, common.cuh): count, per-image exclusive scan, fill -------------------------------------------------
+__device__ __forceinline__ uint32_t key_cell(const KeyIn& k, const KeyGrid& g) {
+    const int cx = min((int)k.x >> 4, g.cw - 1), cy = min((int)k.y >> 4, g.ch - 1);
+    return (uint32_t)k.tgt * (uint32_t)(g.cw * g.ch) + (uint32_t)(cy * g.cw + cx);
+}
+__global__ void key_grid_count_kernel(const KeyIn* __restrict__ keys, const uint32_t* __restrict__ key_img, uint32_t n_keys, KeyGrid g) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keys) return;
+    atomicAdd(g.count + (size_t)key_img[k] * g.cells_per_image + key_cell(keys[k], g), 1u);
+}
+// one CTA per image: exclusive scan of its cell counts (offsets are relative to the image's first key)
+__global__ void __launch_bounds__(1024) key_grid_scan_kernel(KeyGrid g) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const uint32_t* in = g.count + (size_t)blockIdx.x * g.cells_per_image;
+    uint32_t* out = g.offset + (size_t)blockIdx.x * g.cells_per_image;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < g.cells_per_image; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < g.cells_per_image ? in[i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) warp_sums[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const uint32_t before = carry + (wid ? warp_sums[wid - 1] : 0u);
+        if (i < g.cells_per_image) out[i] = before + s - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + s;
+        __syncthreads();
+    }
+}
+__global__ void key_grid_fill_kernel(const KeyIn* __restrict__ keys, const uint32_t* __restrict__ key_img, const uint32_t* __restrict__ key_first,
+                                     uint32_t n_keys, KeyGrid g) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keys) return;
+    const uint32_t img = key_img[k];
+    const size_t cell = (size_t)img * g.cells_per_image + key_cell(keys[k], g);
+    const uint32_t pos = atomicAdd(g.cursor + cell, 1u);
+    g.cell_keys[key_first[img] + g.offset[cell] + pos] = k;
+}
+
 __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restrict__ targets, int n_targets,
                                                          const float* __restrict__ tables, const KeyIn* __restrict__ keys,
                                                          const uint32_t* __restrict__ key_img,
                                                          const uint32_t* __restrict__ key_first, uint32_t n_keys,
                                                          const float* __restrict__ orientation, float* __restrict__ desc,
-                                                         const float2* __restrict__ grad_cache) {
+                                                         const float2* __restrict__ grad_cache, const KeyGrid grid) {
     __shared__ float s_val[4][kWin * kWin];
+    __shared__ uint32_t s_hit[4][2][kMaxGridHits];   // overlapping predecessors found through the grid: unsorted, sorted
     __shared__ uint16_t s_bin[4][kWin * kWin];
+    __shared__ float s_w[4][kWin * kWin];   // this key's weight table: every overlapping predecessor reads it once per covered pixel
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_keys; k += warps) {
@@ -239,7 +302,11 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
         const uint32_t img = key_img[k];
         const LevelRef T = targets[key.tgt];
         const float* G = T.base + (size_t)img * T.stride;
-        const float* W = tables + ((size_t)img * n_targets + key.tgt) * (kWin * kWin);  // W[y*16 + x]
+        const float* Wg = tables + ((size_t)img * n_targets + key.tgt) * (kWin * kWin);  // W[y*16 + x]
+        float* W = s_w[wib];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) W[lane + 32 * j] = Wg[lane + 32 * j];
+        __syncwarp();
         const int x0 = key.x - kRegion, y0 = key.y - kRegion;
 
         // lane owns window pixels s = lane + 32*j, s = wx*16 + wy
@@ -255,44 +322,115 @@ __global__ void __launch_bounds__(128) descriptor_kernel(const LevelRef* __restr
             }
         }
         // replay earlier keypoints of this image and level whose window overlaps, in vector order
+        auto apply_overlap = [&](int mx, int my, float theta) {
+            // This lane's pixels are (wx, wy) = (2j + (lane >> 4), lane & 15): its row inside the earlier window is the same
+            // for all eight, its column advances by two.  No branch per pixel: the table index is clamped and the two
+            // additions are selected (the sums only change where the windows overlap).
+            const int mx0 = mx - kRegion, my0 = my - kRegion;
+            const int ly = y0 + (lane & 15) - my0;
+            const bool row_ok = (unsigned)ly < (unsigned)kWin;
+            const int lx0 = x0 + (lane >> 4) - mx0;
+            const float* wrow = W + (row_ok ? ly : 0) * kWin;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int lx = lx0 + 2 * j;
+                const bool ok = row_ok && (unsigned)lx < (unsigned)kWin;
+                const float wv = wrow[ok ? lx : 0];
+                O[j] = ok ? O[j] + theta : O[j];
+                M[j] = ok ? M[j] + wv : M[j];
+            }
+        };
+        bool use_scan = grid.count == nullptr;
+        if (!use_scan) {
+            // candidates: the keys of the 3 x 3 cells around this key's cell (same image, same target level), unordered
+            const uint32_t* cnt = grid.count + (size_t)img * grid.cells_per_image + (size_t)key.tgt * grid.cw * grid.ch;
+            const uint32_t* off = grid.offset + (size_t)img * grid.cells_per_image + (size_t)key.tgt * grid.cw * grid.ch;
+            const int cx = key.x >> 4, cy = key.y >> 4;
+            uint32_t* hits = s_hit[wib][0];
+            uint32_t* sorted = s_hit[wib][1];
+            uint32_t n_hit = 0;
+            for (int dy = -1; dy <= 1 && n_hit <= kMaxGridHits; ++dy) {
+                const int yy = cy + dy;
+                if (yy < 0 || yy >= grid.ch) continue;
+                for (int dx = -1; dx <= 1 && n_hit <= kMaxGridHits; ++dx) {
+                    const int xx = cx + dx;
+                    if (xx < 0 || xx >= grid.cw) continue;
+                    const uint32_t cell = (uint32_t)(yy * grid.cw + xx);
+                    const uint32_t c_n = cnt[cell], c_off = key_first[img] + off[cell];
+                    for (uint32_t base = 0; base < c_n; base += 32) {
+                        const uint32_t i = base + lane;
+                        uint32_t m = 0xffffffffu;
+                        bool hit = false;
+                        if (i < c_n) {
+                            m = grid.cell_keys[c_off + i];
+                            if (m < k) {
+                                const KeyIn km = keys[m];
+                                const int ddx = (int)km.x - (int)key.x, ddy = (int)km.y - (int)key.y;
+                                hit = ddx > -kWin && ddx < kWin && ddy > -kWin && ddy < kWin;
+                            }
+                        }
+                        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                        const uint32_t slot = n_hit + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+                        if (hit && slot < kMaxGridHits) hits[slot] = m;
+                        n_hit += (uint32_t)__popc(ballot);
+                    }
+                }
+            }
+            if (n_hit > kMaxGridHits) {
+                use_scan = true;   // a crowd (hundreds of windows over one spot): the full scan below handles any number
+            } else if (n_hit) {
+                __syncwarp();
+                // vector order = ascending key index: rank sort (indices are distinct)
+                for (uint32_t e = lane; e < n_hit; e += 32) {
+                    const uint32_t v = hits[e];
+                    uint32_t rank = 0;
+                    for (uint32_t i = 0; i < n_hit; ++i) rank += hits[i] < v ? 1u : 0u;
+                    sorted[rank] = v;
+                }
+                __syncwarp();
+                for (uint32_t base = 0; base < n_hit; base += 32) {
+                    const uint32_t i = base + lane;
+                    KeyIn km = key;
+                    float th = 0.0f;
+                    if (i < n_hit) { km = keys[sorted[i]]; th = orientation[sorted[i]]; }
+                    const uint32_t n_here = min(32u, n_hit - base);
+                    for (uint32_t src = 0; src < n_here; ++src)
+                        apply_overlap(__shfl_sync(0xffffffffu, (int)km.x, src), __shfl_sync(0xffffffffu, (int)km.y, src), __shfl_sync(0xffffffffu, th, src));
+                }
+                __syncwarp();
+            }
+        }
+        if (use_scan) {
         const uint32_t first = key_first[img];
         constexpr int kAhead = 4;  // key chunks loaded per step: their global-load latencies overlap
         for (uint32_t base0 = first; base0 < k; base0 += 32 * kAhead) {
             KeyIn kmv[kAhead];
+            float thv[kAhead];   // the earlier keys' orientations travel with them (no dependent load per overlap)
 #pragma unroll
             for (int c = 0; c < kAhead; ++c) {
                 const uint32_t m = base0 + 32 * c + lane;
                 kmv[c] = keys[m < k ? m : k];
+                thv[c] = orientation[m < k ? m : k];
             }
 #pragma unroll
             for (int c = 0; c < kAhead; ++c) {
-            const uint32_t base = base0 + 32 * c;
-            if (base >= k) break;
-            const uint32_t m = base + lane;
-            const KeyIn km = kmv[c];
-            bool hit = false;
-            if (m < k) {
-                const int ddx = (int)km.x - (int)key.x, ddy = (int)km.y - (int)key.y;
-                hit = km.tgt == key.tgt && ddx > -kWin && ddx < kWin && ddy > -kWin && ddy < kWin;
-            }
-            unsigned ballot = __ballot_sync(0xffffffffu, hit);
-            while (ballot) {
-                const int src = __ffs(ballot) - 1;
-                ballot &= ballot - 1;
-                const int mx0 = __shfl_sync(0xffffffffu, (int)km.x, src) - kRegion;
-                const int my0 = __shfl_sync(0xffffffffu, (int)km.y, src) - kRegion;
-                const float theta = orientation[base + src];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int s = lane + 32 * j, wx = s >> 4, wy = s & 15;
-                    const int lx = x0 + wx - mx0, ly = y0 + wy - my0;  // position inside the earlier window
-                    if (lx >= 0 && lx < kWin && ly >= 0 && ly < kWin) {
-                        O[j] = O[j] + theta;
-                        M[j] = M[j] + W[ly * kWin + lx];
-                    }
+                const uint32_t base = base0 + 32 * c;
+                if (base >= k) break;
+                const uint32_t m = base + lane;
+                const KeyIn km = kmv[c];
+                bool hit = false;
+                if (m < k) {
+                    const int ddx = (int)km.x - (int)key.x, ddy = (int)km.y - (int)key.y;
+                    hit = km.tgt == key.tgt && ddx > -kWin && ddx < kWin && ddy > -kWin && ddy < kWin;
+                }
+                unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                while (ballot) {
+                    const int src = __ffs(ballot) - 1;
+                    ballot &= ballot - 1;
+                    apply_overlap(__shfl_sync(0xffffffffu, (int)km.x, src), __shfl_sync(0xffffffffu, (int)km.y, src), __shfl_sync(0xffffffffu, thv[c], src));
                 }
             }
-            }
+        }
         }
         const float theta = orientation[k];
 #pragma unroll
@@ -358,11 +496,25 @@ int launch_orientation(const LevelRef* targets_dev, int n_targets, const KeyIn* 
 
 int launch_descriptors(const LevelRef* targets_dev, int n_targets, const float* tables, const KeyIn* keys,
                        const uint32_t* key_img, const uint32_t* key_first, uint32_t n_keys, const float* orientation,
-                       float* desc, const float2* grad_cache, cudaStream_t s, uint64_t* launches) {
+                       float* desc, const float2* grad_cache, const KeyGrid* grid, int batch, cudaStream_t s, uint64_t* launches) {
     if (n_keys == 0) return 0;
+    KeyGrid g{};
+    static const bool grid_off = getenv("SIFT_GPU_NO_KEY_GRID") != nullptr;
+    // (one CTA per image scans the cell counts: worth it for video-sized levels, not for the 400 k cells of a 7680x4320 one)
+    if (grid && grid->count && !grid_off && grid->cells_per_image <= 32768u) {
+        g = *grid;
+        const size_t words = (size_t)batch * g.cells_per_image;
+        SIFT_CUDA_TRY(cudaMemsetAsync(g.count, 0, sizeof(uint32_t) * words, s));
+        SIFT_CUDA_TRY(cudaMemsetAsync(g.cursor, 0, sizeof(uint32_t) * words, s));
+        const unsigned kb = (n_keys + 255) / 256;
+        key_grid_count_kernel<<<kb, 256, 0, s>>>(keys, key_img, n_keys, g);
+        key_grid_scan_kernel<<<batch, 1024, 0, s>>>(g);
+        key_grid_fill_kernel<<<kb, 256, 0, s>>>(keys, key_img, key_first, n_keys, g);
+        if (launches) *launches += 3;
+    }
     const unsigned blocks = (unsigned)((n_keys + 3) / 4);
     descriptor_kernel<<<blocks < 148u * 8u ? blocks : 148u * 8u, 128, 0, s>>>(targets_dev, n_targets, tables, keys, key_img,
-                                                                               key_first, n_keys, orientation, desc, grad_cache);
+                                                                               key_first, n_keys, orientation, desc, grad_cache, g);
     if (launches) ++*launches;
     SIFT_CUDA_TRY(cudaGetLastError());
     return 0;

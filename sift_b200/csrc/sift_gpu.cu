@@ -243,6 +243,8 @@ struct Slot {
     float2* d_grad = nullptr;     // per key: the 256 (magnitude, orientation) pairs of its window (orientation kernel -> descriptor kernel)
     float* d_tables = nullptr;
     size_t tables_cap = 0;
+    KeyGrid grid{};               // descriptor kernel's spatial index of the pass's keys (grown with the tables / the key capacity)
+    size_t grid_words = 0, grid_keys = 0;
     // state of the pass in flight
     Plan* plan = nullptr;
     std::vector<ChunkImage> imgs;
@@ -1003,13 +1005,38 @@ static int end_replay_and_enqueue_stage_b(sift_gpu_ctx* c, Slot& S, int slot_ind
             CTX_CUDA(cudaMalloc(&S.d_tables, sizeof(float) * tables_need));
             S.tables_cap = tables_need;
         }
+        // key grid: 16-pixel cells over the largest target level, per image and target
+        {
+            int tw = 1, th = 1;
+            for (size_t t = 0; t < p->target_w.size(); ++t) { tw = std::max(tw, p->target_w[t]); th = std::max(th, p->target_h[t]); }
+            S.grid.cw = (tw + 15) / 16;
+            S.grid.ch = (th + 15) / 16;
+            S.grid.cells_per_image = (uint32_t)(n_targets * S.grid.cw * S.grid.ch);
+            const size_t words = (size_t)nb * S.grid.cells_per_image;
+            if (words > S.grid_words) {
+                cudaFree(S.grid.count); cudaFree(S.grid.offset); cudaFree(S.grid.cursor);
+                S.grid.count = S.grid.offset = S.grid.cursor = nullptr;
+                S.grid_words = 0;
+                CTX_CUDA(cudaMalloc(&S.grid.count, sizeof(uint32_t) * words));
+                CTX_CUDA(cudaMalloc(&S.grid.offset, sizeof(uint32_t) * words));
+                CTX_CUDA(cudaMalloc(&S.grid.cursor, sizeof(uint32_t) * words));
+                S.grid_words = words;
+            }
+            if (n_keys > S.grid_keys) {
+                cudaFree(S.grid.cell_keys);
+                S.grid.cell_keys = nullptr;
+                S.grid_keys = 0;
+                CTX_CUDA(cudaMalloc(&S.grid.cell_keys, sizeof(uint32_t) * S.key_cap));
+                S.grid_keys = S.key_cap;
+            }
+        }
         CTX_TRY(launch_orientation(ps.targets_dev, n_targets, S.d_keys, S.d_key_img, (uint32_t)n_keys, S.d_orient, S.d_npeaks, S.d_peaks, S.d_grad, s, L));
     }
     CTX_CUDA(cudaEventRecord(S.ev[8], s));
     if (n_keys) {
         CTX_TRY(launch_weight_tables(ps.targets_dev, n_targets, c->d_taps + c->w16_blur.tap_off, c->w16_blur.r, S.d_tables, c->fma, nb, s, L));
         CTX_TRY(launch_descriptors(ps.targets_dev, n_targets, S.d_tables, S.d_keys, S.d_key_img, S.d_key_first, (uint32_t)n_keys, S.d_orient,
-                                   S.d_desc, S.d_grad, s, L));
+                                   S.d_desc, S.d_grad, &S.grid, nb, s, L));
     }
     CTX_CUDA(cudaEventRecord(S.ev[9], s));
     if (n_keys) {
@@ -1111,7 +1138,8 @@ static int redo_with_extra_orientations(sift_gpu_ctx* c, Slot& S, int slot_index
         CTX_CUDA(cudaMemcpyAsync(S.d_key_first, S.h_key_first, sizeof(uint32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, s));
         CTX_CUDA(cudaMemcpyAsync(S.d_orient, S.h_orient, sizeof(float) * n_keys, cudaMemcpyHostToDevice, s));
         CTX_TRY(launch_descriptors(ps.targets_dev, (int)ps.targets_host.size(), S.d_tables, S.d_keys, S.d_key_img, S.d_key_first, (uint32_t)n_keys,
-                                   S.d_orient, S.d_desc, nullptr /* another key list: recompute the gradients */, s, &S.launches));
+                                   S.d_orient, S.d_desc, nullptr /* another key list: recompute the gradients */,
+                                   n_keys <= S.grid_keys ? &S.grid : nullptr, (int)S.imgs.size(), s, &S.launches));
         CTX_CUDA(cudaMemcpyAsync(S.h_desc, S.d_desc, sizeof(float) * kDescLen * n_keys, cudaMemcpyDeviceToHost, s));
     }
     CTX_CUDA(cudaStreamSynchronize(s));
@@ -1268,6 +1296,7 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
         cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFree(S.d_slice); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv);
         cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_key_first); cudaFree(S.d_orient); cudaFree(S.d_npeaks);
         cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_grad); cudaFree(S.d_tables);
+        cudaFree(S.grid.count); cudaFree(S.grid.offset); cudaFree(S.grid.cursor); cudaFree(S.grid.cell_keys);
         cudaFreeHost(S.h_keys); cudaFreeHost(S.h_key_img); cudaFreeHost(S.h_key_first); cudaFreeHost(S.h_orient); cudaFreeHost(S.h_npeaks);
         for (auto& e : S.ev) if (e) cudaEventDestroy(e);
         for (auto& e : S.ev_join) if (e) cudaEventDestroy(e);
