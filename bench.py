@@ -432,7 +432,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1536, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=4096, help="frames per step per GPU (BASELINE config 5: a batch of 4096 frames per shard)")
     ap.add_argument("--frames", type=int, default=64, help="distinct synthetic frames per GPU (cycled)")
     ap.add_argument("--device-batch", type=int, default=192, help="frames per device pass (ctx max_batch); several passes are in flight")
     ap.add_argument("--flags", type=int, default=0, help="SIFT_GPU_FLAG_* bits (1 canonical order, 4 FMA blur)")
