@@ -776,7 +776,7 @@ static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, 
         t = n;
     };
     auto t_ph = tick();
-    // the device compacts survivors in canonical order (compact_survivors_kernel): `canon` ascends
+    // the device compacts survivors in canonical order (survivors_count / offsets / write kernels, eliminate.cu): `canon` ascends
     const Surv* S = surv_in;
     lap(0, t_ph);
     // first cleanup over all candidates
