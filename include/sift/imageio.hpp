@@ -2,8 +2,8 @@
 // reference's scalar float image is band 0 of the file, raw 0..255 — the R channel of a colour image, the grey values of
 // a grey one — and cv::imread(..., CV_LOAD_IMAGE_COLOR) gives the three-channel copy the overlay is drawn on.
 // Decode stays on the host side of the C ABI (north_star):
-//   * PNG: 8-bit grey / RGB / palette / with alpha, non-interlaced — chunk parser and the five scanline filters here,
-//     inflate by zlib;
+//   * PNG: 8- or 16-bit grey / RGB / with alpha, 8-bit palette, non-interlaced — chunk parser and the five scanline filters
+//     here, inflate by zlib; 16-bit samples reach the float image unscaled (0..65535), as importImage leaves them;
 //   * JPEG: the toolkit's nvJPEG (the image has no libjpeg headers), decoded to interleaved RGB and copied back;
 //   * binary PGM / PPM.
 // The overlay goes out as PNG (`<image>_orientation.png`, main.cpp:76) or PPM.
@@ -30,6 +30,8 @@ extern "C" {
 // C entry points for bindings and tests.  rgb = width*height*3 bytes, caller-allocated (call with rgb = NULL to get the size).
 // Returns 0, or -1 with a message in err (if err_len > 0).
 int sift_host_read_image(const char* path, unsigned char* rgb, int* width, int* height, char* err, int err_len);
+// band 0 as readImage() delivers it to sift::Sift::calculate (width*height floats; band0 = NULL to get the size)
+int sift_host_read_band0(const char* path, float* band0, int* width, int* height, char* err, int err_len);
 int sift_host_write_png(const char* path, const unsigned char* rgb, int width, int height);
 }
 #endif  // SIFT_IMAGEIO_HPP

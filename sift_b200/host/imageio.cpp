@@ -26,12 +26,17 @@ bool slurp(const std::string& path, Bytes* out) {
     return true;
 }
 
-void fill(const unsigned char* rgb, int w, int h, Image* band0, ColorImage* color) {
+// band0_16: the file's own 16-bit samples of band 0 (what vigra::importImage copies into the float image unscaled), or empty
+void fill(const unsigned char* rgb, const std::vector<uint16_t>& band0_16, int w, int h, Image* band0, ColorImage* color) {
     *band0 = Image(w, h);
     *color = ColorImage(w, h);
     std::memcpy(color->rgb.data(), rgb, (size_t)w * (size_t)h * 3);
     f32_t* px = band0->data();
-    for (size_t i = 0, n = (size_t)w * (size_t)h; i < n; ++i) px[i] = (f32_t)rgb[3 * i];   // band 0
+    const size_t n = (size_t)w * (size_t)h;
+    if (band0_16.size() == n)
+        for (size_t i = 0; i < n; ++i) px[i] = (f32_t)band0_16[i];
+    else
+        for (size_t i = 0; i < n; ++i) px[i] = (f32_t)rgb[3 * i];   // band 0
 }
 
 // ---- binary PGM / PPM ------------------------------------------------------------------------------------------------
@@ -68,7 +73,7 @@ int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
-bool decode_png(const Bytes& b, Bytes* rgb, int* w, int* h, std::string* err) {
+bool decode_png(const Bytes& b, Bytes* rgb, std::vector<uint16_t>* band0_16, int* w, int* h, std::string* err) {
     size_t at = 8;
     uint32_t width = 0, height = 0;
     int depth = 0, ctype = -1, interlace = 0;
@@ -88,16 +93,18 @@ bool decode_png(const Bytes& b, Bytes* rgb, int* w, int* h, std::string* err) {
     }
     const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!width || !height || width > 65535 || height > 65535 || !channels) { *err = "unsupported PNG header"; return false; }
-    if (depth != 8 || interlace) { *err = "unsupported PNG (8 bits per sample, non-interlaced only)"; return false; }
+    if ((depth != 8 && depth != 16) || (depth == 16 && ctype == 3) || interlace) { *err = "unsupported PNG (8 or 16 bits per sample, non-interlaced only)"; return false; }
     if (ctype == 3 && plte.size() < 3) { *err = "palette PNG without PLTE"; return false; }
-    const size_t stride = (size_t)width * channels;
+    const int bps = depth / 8;                       // bytes per sample; 16-bit samples are big-endian
+    const size_t stride = (size_t)width * channels * bps;
     Bytes raw((stride + 1) * height);
     uLongf raw_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) { *err = "PNG inflate failed"; return false; }
     // undo the scanline filters in place (bpp = bytes per complete pixel)
-    const int bpp = channels;
+    const int bpp = channels * bps;
     Bytes prev(stride, 0);
     rgb->resize((size_t)width * height * 3);
+    if (bps == 2 && band0_16) band0_16->resize((size_t)width * height);
     for (uint32_t y = 0; y < height; ++y) {
         unsigned char* line = &raw[(stride + 1) * y + 1];
         const int ft = raw[(stride + 1) * y];
@@ -117,12 +124,13 @@ bool decode_png(const Bytes& b, Bytes* rgb, int* w, int* h, std::string* err) {
         std::memcpy(prev.data(), line, stride);
         unsigned char* out = &(*rgb)[(size_t)y * width * 3];
         for (uint32_t x = 0; x < width; ++x) {
-            const unsigned char* p = line + (size_t)x * channels;
+            const unsigned char* p = line + (size_t)x * channels * bps;   // 16-bit: the high byte is the 8-bit view (cv::imread)
+            if (bps == 2 && band0_16) (*band0_16)[(size_t)y * width + x] = (uint16_t)((p[0] << 8) | p[1]);
             if (ctype == 0 || ctype == 4) { out[3 * x] = out[3 * x + 1] = out[3 * x + 2] = p[0]; }
             else if (ctype == 3) {
                 const size_t e = (size_t)p[0] * 3;
                 for (int k = 0; k < 3; ++k) out[3 * x + k] = e + 2 < plte.size() ? plte[e + k] : 0;
-            } else { out[3 * x] = p[0]; out[3 * x + 1] = p[1]; out[3 * x + 2] = p[2]; }
+            } else { out[3 * x] = p[0]; out[3 * x + 1] = p[bps]; out[3 * x + 2] = p[2 * bps]; }
         }
     }
     *w = (int)width; *h = (int)height;
@@ -157,11 +165,12 @@ bool decode_jpeg(const Bytes& b, Bytes* rgb, int* w, int* h, std::string* err) {
     return ok;
 }
 
-bool decode_any(const std::string& path, Bytes* rgb, int* w, int* h, std::string* err) {
+bool decode_any(const std::string& path, Bytes* rgb, std::vector<uint16_t>* band0_16, int* w, int* h, std::string* err) {
+    if (band0_16) band0_16->clear();
     Bytes b;
     if (!slurp(path, &b)) { *err = "cannot open '" + path + "'"; return false; }
     static const unsigned char png_magic[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    if (b.size() >= 8 && !std::memcmp(b.data(), png_magic, 8)) return decode_png(b, rgb, w, h, err);
+    if (b.size() >= 8 && !std::memcmp(b.data(), png_magic, 8)) return decode_png(b, rgb, band0_16, w, h, err);
     if (b.size() >= 3 && b[0] == 0xff && b[1] == 0xd8) return decode_jpeg(b, rgb, w, h, err);
     if (b.size() >= 7 && b[0] == 'P' && (b[1] == '5' || b[1] == '6')) return decode_pnm(b, rgb, w, h, err);
     *err = "'" + path + "': not a PNG, JPEG or binary PGM/PPM file";
@@ -183,13 +192,14 @@ void put_chunk(std::ofstream& f, const char* type, const unsigned char* data, si
 
 bool readImage(const std::string& path, Image* band0, ColorImage* color, std::string* error) {
     Bytes rgb;
+    std::vector<uint16_t> b16;
     int w = 0, h = 0;
     std::string err;
-    if (!decode_any(path, &rgb, &w, &h, &err)) {
+    if (!decode_any(path, &rgb, &b16, &w, &h, &err)) {
         if (error) *error = err;
         return false;
     }
-    fill(rgb.data(), w, h, band0, color);
+    fill(rgb.data(), b16, w, h, band0, color);
     return true;
 }
 
@@ -224,13 +234,26 @@ int sift_host_read_image(const char* path, unsigned char* rgb, int* width, int* 
     sift::Bytes px;
     int w = 0, h = 0;
     std::string why;
-    if (!path || !sift::decode_any(path, &px, &w, &h, &why)) {
+    if (!path || !sift::decode_any(path, &px, nullptr, &w, &h, &why)) {
         if (err && err_len > 0) { std::strncpy(err, why.c_str(), (size_t)err_len - 1); err[err_len - 1] = 0; }
         return -1;
     }
     if (width) *width = w;
     if (height) *height = h;
     if (rgb) std::memcpy(rgb, px.data(), px.size());
+    return 0;
+}
+int sift_host_read_band0(const char* path, float* band0, int* width, int* height, char* err, int err_len) {
+    sift::Image img;
+    sift::ColorImage color;
+    std::string why;
+    if (!path || !sift::readImage(path, &img, &color, &why)) {
+        if (err && err_len > 0) { std::strncpy(err, why.c_str(), (size_t)err_len - 1); err[err_len - 1] = 0; }
+        return -1;
+    }
+    if (width) *width = (int)img.width();
+    if (height) *height = (int)img.height();
+    if (band0) std::memcpy(band0, img.data(), sizeof(float) * img.size());
     return 0;
 }
 int sift_host_write_png(const char* path, const unsigned char* rgb, int width, int height) {

@@ -304,6 +304,20 @@ def test_cli_image_files_png_and_pnm(built, tmp_path):
     assert lib.sift_host_write_png(str(out).encode(), rgb.ctypes.data, w, h) == 0
     assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), rgb)
     assert np.array_equal(_read_image(lib, out), rgb)
+    # 16-bit grey: band 0 keeps the file's sample values (vigra::importImage does not scale), the colour view is the high byte
+    import ctypes
+
+    g16 = (rng.integers(0, 65536, (h, w))).astype(np.uint16)
+    Image.fromarray(g16, "I;16").save(tmp_path / "g16.png")
+    lib.sift_host_read_band0.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_int]
+    lib.sift_host_read_band0.restype = ctypes.c_int
+    ww, hh = ctypes.c_int(0), ctypes.c_int(0)
+    b0 = np.zeros((h, w), np.float32)
+    assert lib.sift_host_read_band0(str(tmp_path / "g16.png").encode(), b0.ctypes.data, ctypes.byref(ww), ctypes.byref(hh), None, 0) == 0
+    assert (ww.value, hh.value) == (w, h) and np.array_equal(b0, g16.astype(np.float32))
+    assert np.array_equal(_read_image(lib, tmp_path / "g16.png"), np.repeat((g16 >> 8).astype(np.uint8)[:, :, None], 3, 2))
+    assert lib.sift_host_read_band0(str(tmp_path / "rgb.png").encode(), b0.ctypes.data, ctypes.byref(ww), ctypes.byref(hh), None, 0) == 0
+    assert np.array_equal(b0, rgb[:, :, 0].astype(np.float32))
     # not an image / unsupported: an error message, no crash
     (tmp_path / "x.txt").write_bytes(b"hello world, not an image")
     with pytest.raises(ValueError):
