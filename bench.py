@@ -268,8 +268,19 @@ def run_ours(args):
     dev_frames = host_frames.to(dev)  # 64 x 8.3 MB = 531 MB > L2 (126 MB): successive steps cannot be served from L2
     torch.cuda.synchronize()
 
-    g = capi.SiftGpu(DPE, OCTAVES, 1.6, capi.SQRT2_F32, False, max_width=W, max_height=H, max_batch=args.device_batch,
-                     device=local_rank, flags=args.flags)
+    # 192-frame passes x 5 slots take ~145 GB of the B200's 180 GB; on a device with less free memory fall back to smaller passes
+    # (same results, a few per cent slower) instead of failing the run
+    while True:
+        try:
+            g = capi.SiftGpu(DPE, OCTAVES, 1.6, capi.SQRT2_F32, False, max_width=W, max_height=H, max_batch=args.device_batch,
+                             device=local_rank, flags=args.flags)
+            break
+        except capi.SiftGpuError as e:
+            if args.device_batch <= 16:
+                raise
+            print(f"note: context with {args.device_batch}-frame passes does not fit ({e}); trying {args.device_batch // 2}", file=sys.stderr)
+            args.device_batch //= 2
+            torch.cuda.empty_cache()
 
     def descs(base_ptr, memory, step, dtype=capi.DTYPE_F32):
         arr = (capi.Image * B)()
