@@ -140,6 +140,17 @@ int sift_gpu_debug_eliminate(sift_gpu_ctx* ctx, const float* d0, const float* d1
 /* Candidates of image `image_idx` of the last pass, canonical order, with their elimination flag. */
 int sift_gpu_debug_get_candidates(sift_gpu_ctx* ctx, int image_idx, uint16_t* xs, uint16_t* ys, uint16_t* octave,
                                   uint16_t* index, uint8_t* filtered, uint32_t capacity, uint32_t* n);
+/* The host half of Sift::calculate between _eliminateEdgeResponses and _createDecriptors (sift.cpp:37-55: first cleanup sort,
+ * u16 size, orientation-stage bounds test, second cleanup sort, descriptor-stage bounds test) on its own, exactly as
+ * sift_gpu_run executes it between its two device stages, but without a device — so the ordering logic can be tested on
+ * machines that have no GPU.  In: the unfiltered candidates of ONE image of `width` x `height` (input size, before the optional
+ * upsample) in canonical order, `canon[i]` = their position in the candidate vector of `n_candidates` entries (ascending).
+ * Out: the keypoint records in the reference's final vector order (orientation 0, it comes from the device), and the number
+ * of points after the first cleanup.  SIFT_GPU_FLAG_STRICT / _ORDER_CANONICAL in params->flags act as in sift_gpu_run. */
+int sift_gpu_debug_host_replay(const sift_gpu_params* params, int width, int height, uint32_t n_candidates, const uint32_t* canon,
+                               const uint16_t* xs, const uint16_t* ys, const uint8_t* octave, const uint8_t* index,
+                               uint32_t n_unfiltered, sift_gpu_keypoint* kps, uint32_t capacity, uint32_t* n_kps,
+                               uint32_t* n_survivors);
 /* The std::sort(cmpByFilter) permutation the host replays (sift.cpp:37): order[i] = source index. */
 int sift_gpu_debug_sort_order(const uint8_t* filtered, uint32_t n, uint32_t* order);
 /* The same permutation restricted to the unfiltered elements (all the pipeline needs), computed by the sparse

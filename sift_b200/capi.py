@@ -102,6 +102,10 @@ def load():
     L.sift_gpu_debug_sort_order.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.sift_gpu_debug_sort_order_fast.restype = C.c_int
     L.sift_gpu_debug_sort_order_fast.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    L.sift_gpu_debug_host_replay.restype = C.c_int
+    L.sift_gpu_debug_host_replay.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -110,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "sift_gpu_create", "sift_gpu_run", "sift_gpu_destroy", "sift_gpu_last_error", "sift_gpu_get_timings",
     "sift_gpu_version", "sift_gpu_debug_get_level", "sift_gpu_debug_blur", "sift_gpu_debug_reduce",
     "sift_gpu_debug_increase", "sift_gpu_debug_extrema", "sift_gpu_debug_eliminate", "sift_gpu_debug_get_candidates",
-    "sift_gpu_debug_sort_order", "sift_gpu_debug_sort_order_fast",
+    "sift_gpu_debug_sort_order", "sift_gpu_debug_sort_order_fast", "sift_gpu_debug_host_replay",
 ]
 
 
@@ -133,6 +137,27 @@ def sort_order_fast(flags):
     if rc != 0:
         raise SiftGpuError(rc, "sort_order_fast")
     return order[: n.value].copy()
+
+
+def host_replay(width, height, n_candidates, canon, xs, ys, octave, index, *, dogs_per_epoch=3, octaves=3, sigma=1.6,
+                k=SQRT2_F32, subpixel=False, flags=0):
+    """The host half of Sift::calculate between the two device stages (sift.cpp:37-55), run without a device: unfiltered
+    candidates of one image in canonical order in, keypoint records in the reference's final vector order out.
+    Returns (kps as a KP_DTYPE array, n_survivors after the first cleanup)."""
+    canon = np.ascontiguousarray(canon, np.uint32)
+    xs, ys = np.ascontiguousarray(xs, np.uint16), np.ascontiguousarray(ys, np.uint16)
+    octave, index = np.ascontiguousarray(octave, np.uint8), np.ascontiguousarray(index, np.uint8)
+    prm = Params(sigma, k, octaves, dogs_per_epoch, 1 if subpixel else 0, 0, width, height, 1, flags)
+    kps = np.zeros(max(1, canon.size), KP_DTYPE)
+    n, ns = C.c_uint32(), C.c_uint32()
+    rc = load().sift_gpu_debug_host_replay(C.byref(prm), width, height, n_candidates, canon.ctypes.data, xs.ctypes.data,
+                                           ys.ctypes.data, octave.ctypes.data, index.ctypes.data, canon.size,
+                                           kps.ctypes.data, kps.size, C.byref(n), C.byref(ns))
+    if rc == E_PRECONDITION:
+        raise SiftGpuPrecondition(rc, "host_replay")
+    if rc != 0:
+        raise SiftGpuError(rc, "host_replay")
+    return kps[: n.value].copy(), ns.value
 
 
 def results_to_dicts(res):

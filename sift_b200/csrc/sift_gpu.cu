@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <tuple>
 #include <string>
@@ -319,8 +320,9 @@ static int set_error(sift_gpu_ctx* c, int code, const std::string& msg) {
 
 static size_t level_px(int w, int h) { return (size_t)w * (size_t)h; }
 
-// Schedule of Sift::_createDOGs (sift.cpp:381-417): scale labels, radii, taps.
-static int build_schedule(sift_gpu_ctx* c) {
+// Schedule of Sift::_createDOGs (sift.cpp:381-417): scale labels, radii, taps.  Host arithmetic only (no device is touched:
+// sift_gpu_debug_host_replay runs it on machines without one).
+static void build_schedule_host(sift_gpu_ctx* c) {
     const int O = c->O, D = c->D;
     std::vector<float> pool;
     auto add = [&](float sigma) {
@@ -358,8 +360,12 @@ static int build_schedule(sift_gpu_ctx* c) {
             c->dead_blur_r[e][i] = r;
         }
     c->h_taps = pool;
-    CTX_CUDA(cudaMalloc(&c->d_taps, sizeof(float) * pool.size()));
-    CTX_CUDA(cudaMemcpy(c->d_taps, pool.data(), sizeof(float) * pool.size(), cudaMemcpyHostToDevice));
+}
+
+static int build_schedule(sift_gpu_ctx* c) {
+    build_schedule_host(c);
+    CTX_CUDA(cudaMalloc(&c->d_taps, sizeof(float) * c->h_taps.size()));
+    CTX_CUDA(cudaMemcpy(c->d_taps, c->h_taps.data(), sizeof(float) * c->h_taps.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -381,6 +387,29 @@ static void nearest_gaussian(const sift_gpu_ctx* c, float scale, int* o_out, int
             if (cur < lowest) { lowest = cur; bo = o; bi = i; }
         }
     *o_out = bo; *i_out = bi;
+}
+
+// Nearest-Gaussian targets per keypoint class (identical for every slot; only the base pointers differ).  Host arithmetic only.
+static void fill_class_targets(sift_gpu_ctx* c, Plan* p, std::vector<std::pair<int, int>>* target_level_out) {
+    const int O = c->O, D = c->D;
+    p->class_target.assign((size_t)(O * D), -1);
+    std::vector<std::pair<int, int>>& target_level = *target_level_out;
+    for (int e = 0; e < O; ++e)
+        for (int i = 1; i < D - 1; ++i) {
+            int to, ti;
+            nearest_gaussian(c, c->d_scale[e][i], &to, &ti);
+            int slot = -1;
+            for (size_t s = 0; s < target_level.size(); ++s)
+                if (target_level[s] == std::make_pair(to, ti)) slot = (int)s;
+            if (slot < 0) {
+                slot = (int)target_level.size();
+                target_level.push_back(std::make_pair(to, ti));
+                p->target_w.push_back(p->ow[to]);
+                p->target_h.push_back(p->oh[to]);
+            }
+            p->class_target[(size_t)(e * D + i)] = slot;
+            if (ti == D) c->top_needed[to] = true;
+        }
 }
 
 static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
@@ -440,25 +469,8 @@ static Plan* get_plan(sift_gpu_ctx* c, int in_w, int in_h) {
             return p;
         }
     }
-    // nearest-Gaussian targets per keypoint class (identical for every slot; only the base pointers differ)
-    p->class_target.assign((size_t)(O * D), -1);
     std::vector<std::pair<int, int>> target_level;
-    for (int e = 0; e < O; ++e)
-        for (int i = 1; i < D - 1; ++i) {
-            int to, ti;
-            nearest_gaussian(c, c->d_scale[e][i], &to, &ti);
-            int slot = -1;
-            for (size_t s = 0; s < target_level.size(); ++s)
-                if (target_level[s] == std::make_pair(to, ti)) slot = (int)s;
-            if (slot < 0) {
-                slot = (int)target_level.size();
-                target_level.push_back(std::make_pair(to, ti));
-                p->target_w.push_back(p->ow[to]);
-                p->target_h.push_back(p->oh[to]);
-            }
-            p->class_target[(size_t)(e * D + i)] = slot;
-            if (ti == D) c->top_needed[to] = true;
-        }
+    fill_class_targets(c, p, &target_level);
     for (int si = 0; si < c->n_slots; ++si) {
         Slot& S = c->slots[si];
         PlanSlot& ps = p->ps[si];
@@ -1659,6 +1671,38 @@ int sift_gpu_debug_get_candidates(sift_gpu_ctx* c, int image_idx, uint16_t* xs, 
         if (index) index[i] = hc[i].index;
         if (filtered) filtered[i] = hc[i].filtered;
     }
+    return SIFT_GPU_OK;
+}
+
+int sift_gpu_debug_host_replay(const sift_gpu_params* params, int width, int height, uint32_t n_candidates, const uint32_t* canon,
+                               const uint16_t* xs, const uint16_t* ys, const uint8_t* octave, const uint8_t* index, uint32_t n_unfiltered,
+                               sift_gpu_keypoint* kps, uint32_t capacity, uint32_t* n_kps, uint32_t* n_survivors) {
+    if (!params || !n_kps || (n_unfiltered && (!canon || !xs || !ys || !octave || !index)) || (capacity && !kps)) return SIFT_GPU_E_INVALID;
+    if (!(params->octaves > 0) || !(params->dogs_per_epoch >= 3)) return SIFT_GPU_E_ASSERT;
+    if (params->octaves > kMaxOctaves || params->dogs_per_epoch + 1 > kMaxGauss) return SIFT_GPU_E_UNSUPPORTED;
+    if (width < 1 || height < 1) return SIFT_GPU_E_INVALID;
+    // the host-side parts of a context and a plan: nothing here touches a device
+    std::unique_ptr<sift_gpu_ctx> c(new sift_gpu_ctx());
+    c->prm = *params;
+    c->O = params->octaves; c->D = params->dogs_per_epoch; c->G = c->D + 1;
+    build_schedule_host(c.get());
+    std::unique_ptr<Plan> p(new Plan());
+    p->in_w = width; p->in_h = height;
+    octave_dims(c.get(), width, height, p->ow, p->oh);
+    std::vector<std::pair<int, int>> target_level;
+    fill_class_targets(c.get(), p.get(), &target_level);
+    std::vector<Surv> surv(n_unfiltered);
+    for (uint32_t i = 0; i < n_unfiltered; ++i) {
+        if (canon[i] >= n_candidates || (i && canon[i] <= canon[i - 1]) || octave[i] >= c->O || index[i] < 1 || index[i] >= c->D - 1) return SIFT_GPU_E_INVALID;
+        surv[i].canon = canon[i]; surv[i].x = xs[i]; surv[i].y = ys[i]; surv[i].octave = octave[i]; surv[i].index = index[i];
+    }
+    ReplayOut out;
+    replay_image(c.get(), p.get(), n_candidates, surv.data(), n_unfiltered, &out);
+    if (n_survivors) *n_survivors = out.n_survivors;
+    *n_kps = (uint32_t)out.kps.size();
+    if (out.status != SIFT_GPU_OK) return out.status;
+    if (out.kps.size() > capacity) return SIFT_GPU_E_CAPACITY;
+    std::copy(out.kps.begin(), out.kps.end(), kps);
     return SIFT_GPU_OK;
 }
 

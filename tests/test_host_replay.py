@@ -1,0 +1,81 @@
+"""The host half of the product path — what sift_gpu_run does between its two device stages: the reference's first
+cleanup sort with its u16 size, the orientation-stage bounds test, the second cleanup sort and the descriptor-stage
+bounds test (sift.cpp:37-55, :65-70, :173-178) — against the pinned oracle, on the CPU (no GPU needed).
+
+`sift_gpu_debug_host_replay` (include/sift_gpu.h) runs exactly the function the pipeline runs per image
+(`replay_image`, sift_b200/csrc/sift_gpu.cu) on a candidate list supplied by the caller.  Here that list is the
+oracle's own `_eliminateEdgeResponses` output, so the test isolates the ordering logic: the unstable std::sort replay
+(order_replay.h), the truncation and the bounds tests.  The oracle is only the checker."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import ref_cases as rc
+from sift_b200 import capi
+
+# "negative" leaves keypoints with several orientation peaks: the reference then appends copies behind the vector
+# (sift.cpp:194-200), which the pipeline handles in a second replay once the device has delivered the peaks
+# (redo_with_extra_orientations, GPU test test_extra_orientation_peaks_*); the single-pass entry point cannot see them.
+CASES = [n for n in rc.CASES if n != "negative"]
+
+
+def oracle_case(name):
+    make, p, throws, _ = rc.CASES[name]
+    img = make()
+    o = ol.Oracle(p["dpe"], p["octaves"], p["sigma"], p["k"], p["subpixel"], strict=False)
+    kp = o.calculate(img)
+    return img, o, kp, p, throws
+
+
+def replay(img, o, p, flags=0):
+    c = o.candidates()
+    keep = np.flatnonzero(c["filtered"] == 0).astype(np.uint32)
+    h, w = img.shape
+    return capi.host_replay(w, h, c["x"].size, keep, c["x"][keep], c["y"][keep], c["octave"][keep].astype(np.uint8),
+                            c["index"][keep].astype(np.uint8), dogs_per_epoch=p["dpe"], octaves=p["octaves"],
+                            sigma=p["sigma"], k=p["k"], subpixel=p["subpixel"], flags=flags)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_replay_reproduces_the_oracles_vector_order(name):
+    img, o, kp, p, throws = oracle_case(name)
+    got, n_surv = replay(img, o, p)
+    assert n_surv == o.survivors()["x"].size                      # (uint16_t) size after the first cleanup (sift.cpp:41)
+    assert got.size == kp["x"].size
+    for f in ("x", "y", "octave", "index", "filtered"):
+        assert np.array_equal(got[f], kp[f]), f"keypoint field {f}: the vector order differs from the reference's"
+    assert np.array_equal(got["scale"], kp["scale"])              # DoG scale label, bit for bit
+    assert np.array_equal(got["desc_len"].astype(np.int32), kp["desc_len"])
+    if throws:                                                    # the dead blur of sift.cpp:184 throws in the reference
+        with pytest.raises(capi.SiftGpuPrecondition):
+            replay(img, o, p, flags=capi.FLAG_STRICT)
+    else:
+        strict, _ = replay(img, o, p, flags=capi.FLAG_STRICT)
+        assert np.array_equal(strict, got)
+
+
+def test_host_replay_u16_wrap_drops_what_the_reference_drops():
+    """More than 65535 unfiltered candidates: the reference keeps (uint16_t)count points of the sorted vector."""
+    img, o, kp, p, _ = oracle_case("u16_wrap")
+    n_unf = int((o.candidates()["filtered"] == 0).sum())
+    assert n_unf > 65535
+    got, n_surv = replay(img, o, p)
+    assert n_surv == n_unf % 65536 == o.survivors()["x"].size
+    assert got.size == kp["x"].size
+
+
+def test_host_replay_canonical_mode_keeps_the_set():
+    img, o, kp, p, _ = oracle_case("ragged")
+    got, _ = replay(img, o, p, flags=capi.FLAG_ORDER_CANONICAL)
+    ref = sorted(zip(kp["octave"].tolist(), kp["index"].tolist(), kp["y"].tolist(), kp["x"].tolist()))
+    mine = sorted(zip(got["octave"].tolist(), got["index"].tolist(), got["y"].tolist(), got["x"].tolist()))
+    assert ref == mine
+
+
+def test_host_replay_rejects_bad_lists():
+    with pytest.raises(capi.SiftGpuError):   # canon must ascend
+        capi.host_replay(64, 64, 10, [3, 2], [20, 21], [20, 21], [0, 0], [1, 1])
+    with pytest.raises(capi.SiftGpuError):   # index outside the scanned layers
+        capi.host_replay(64, 64, 10, [1], [20], [20], [0], [0])
+    got, ns = capi.host_replay(64, 64, 10, [], [], [], [], [])
+    assert got.size == 0 and ns == 0
