@@ -10,40 +10,39 @@
 // Key: 0 = unfiltered (sorts first), 1 = filtered.  comp(a, b) == (a == 0 && b == 1).
 // tests/test_abi_cpu.py compares the result with the real std::sort over many sizes and densities.
 //
-// Which std::sort: the dense hand-off below calls libstdc++'s own std::__introsort_loop, an internal whose signature has
-// been stable from GCC 4.9 to 15 (checked range below); outside that range, or on another standard library, every segment
-// takes the sparse simulation, which implements the same algorithm (libstdc++'s: median of first+1 / mid / last-1 moved to
-// first, unguarded Hoare partition, 16-element threshold, depth limit 2*lg n) and gives the same permutation, only slower.
-// The order contract is therefore "GNU libstdc++'s introsort" — the library the reference's shipped binary (GCC 7.1) and
-// this build (GCC 13) both use.
+// Which std::sort: GNU libstdc++'s (median of first+1 / mid / last-1 moved to first, unguarded Hoare partition, 16-element
+// threshold, depth limit 2*lg n, heap sort below it) — the library the reference's shipped binary (GCC 7.1) and this build
+// (GCC 13) both use; the algorithm has not changed from GCC 4.9 to 15.  Everything here is written out against that
+// description and needs only public API (std::partial_sort for the heap fallback); with -DSIFT_ORDER_REPLAY_LIBSTDCXX_DENSE
+// dense segments are handed to libstdc++'s own std::__introsort_loop instead (a cross-check used by the tests, slower).
 #pragma once
 #include <algorithm>
 #include <cstdint>
 #include <vector>
 
-#if defined(__GLIBCXX__) && defined(_GLIBCXX_RELEASE) && _GLIBCXX_RELEASE >= 5 && _GLIBCXX_RELEASE <= 15
-#define SIFT_ORDER_REPLAY_LIBSTDCXX 1
-#endif
-
 namespace siftgpu {
 
 class SparseFilterSort {
    public:
-    // zero_pos: ascending positions (indices into the n-element vector) of the unfiltered elements.
-    // Returns, in post-sort order, the index into zero_pos of each unfiltered element.
+    // zero_pos[0, m): ascending positions (indices into the n-element vector) of the unfiltered elements.
+    // Returns, in post-sort order, the index into zero_pos of each unfiltered element (valid until the next run).
     // State is two small parallel arrays (position, id) kept sorted by position: nothing of size n is ever touched.
-    std::vector<uint32_t> run(uint32_t n, const std::vector<uint32_t>& zero_pos) {
-        zp_ = zero_pos;
-        id_.resize(zp_.size());
-        for (size_t i = 0; i < zp_.size(); ++i) id_[i] = (uint32_t)i;
+    const std::vector<uint32_t>& run(uint32_t n, const uint32_t* zero_pos, size_t m) {
+        zp_.assign(zero_pos, zero_pos + m);
+        id_.resize(m);
+        for (size_t i = 0; i < m; ++i) id_[i] = (uint32_t)i;
         if (n > 1) {
             int lg = 0;
             for (uint32_t v = n; v > 1; v >>= 1) ++lg;  // std::__lg
-            introsort_loop(0, (int64_t)n, 2 * lg, 0, zp_.size());
+            introsort_loop(0, (int64_t)n, 2 * lg, 0, m);
         }
         // __final_insertion_sort never lets an element pass an equal one: the unfiltered come out in position order
         return id_;
     }
+    const std::vector<uint32_t>& run(uint32_t n, const std::vector<uint32_t>& zero_pos) { return run(n, zero_pos.data(), zero_pos.size()); }
+
+    // A segment is materialised once this fraction of it is unfiltered (dense_num / dense_den; measured optimum).
+    int dense_num = 1, dense_den = 2;
 
    private:
     std::vector<uint32_t> zp_;   // positions of the unfiltered elements, ascending; every active segment owns a slice
@@ -66,7 +65,7 @@ class SparseFilterSort {
                 heap_fallback(f, l, za, zb);
                 return;
             }
-            if ((zb - za) * 2 >= (size_t)(l - f)) {  // half unfiltered: cheaper to let libstdc++ run on the real thing
+            if ((zb - za) * (size_t)dense_den >= (size_t)(l - f) * (size_t)dense_num) {  // cheaper to sort the real thing from here on
                 dense_segment(f, l, depth, za, zb);
                 return;
             }
@@ -79,45 +78,65 @@ class SparseFilterSort {
         }
     }
 
-    // std::__partial_sort(first, last, last): materialise the segment and let libstdc++ do it
+    static bool word_less(uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); }
+
+    // std::__partial_sort(first, last, last): materialise the segment and let the library's heap sort do it
     void heap_fallback(int64_t f, int64_t l, size_t za, size_t zb) {
-        std::vector<uint32_t> e((size_t)(l - f), 0x80000000u);
-        for (size_t i = za; i < zb; ++i) e[(size_t)((int64_t)zp_[i] - f)] = id_[i];
-        std::partial_sort(e.begin(), e.end(), e.end(), [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
-        size_t z = za;
-        for (int64_t p = f; p < l; ++p) {
-            const uint32_t v = e[(size_t)(p - f)];
-            if (!(v >> 31)) { zp_[z] = (uint32_t)p; id_[z] = v; ++z; }
-        }
+        materialise(f, l, za, zb);
+        std::partial_sort(seg_.begin(), seg_.end(), seg_.end(), word_less);
+        collect(f, l, za, zb);
     }
 
-    // A segment in which at least half of the elements is unfiltered is materialised as (filtered bit | id) words and sorted
-    // for real.  With libstdc++ (checked release range above) by its own std::__introsort_loop with the depth budget left at
-    // this point of the recursion — the same code std::sort would be running here; elsewhere by the restatement below
-    // (SIFT_ORDER_REPLAY_OWN_DENSE selects it explicitly; tests compare both with std::sort).
-    void dense_segment(int64_t f, int64_t l, int depth, size_t za, size_t zb) {
+    // segment [f, l) as words: bit 31 = filtered, low bits = id of the unfiltered element sitting there
+    void materialise(int64_t f, int64_t l, size_t za, size_t zb) {
         seg_.assign((size_t)(l - f), 0x80000000u);
         for (size_t i = za; i < zb; ++i) seg_[(size_t)((int64_t)zp_[i] - f)] = id_[i];
-#if defined(SIFT_ORDER_REPLAY_LIBSTDCXX) && !defined(SIFT_ORDER_REPLAY_OWN_DENSE)
-        auto comp = [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); };
-        std::__introsort_loop(seg_.begin(), seg_.end(), (long)depth, __gnu_cxx::__ops::__iter_comp_iter(comp));
-#else
-        dense_introsort(seg_.data(), seg_.data() + seg_.size(), depth);
-#endif
-        size_t z = za;
-        for (int64_t p = f; p < l; ++p) {
-            const uint32_t v = seg_[(size_t)(p - f)];
-            if (!(v >> 31)) { zp_[z] = (uint32_t)p; id_[z] = v; ++z; }
+    }
+    // back to (position, id) pairs in position order; branch-free compaction through the scratch arrays
+    void collect(int64_t f, int64_t l, size_t za, size_t zb) {
+        const size_t len = (size_t)(l - f);
+        tp_.resize(len + 1);
+        ti_.resize(len + 1);
+        size_t z = 0;
+        for (size_t p = 0; p < len; ++p) {
+            const uint32_t v = seg_[p];
+            tp_[z] = (uint32_t)(f + (int64_t)p);
+            ti_[z] = v;
+            z += (v >> 31) ^ 1u;
         }
+        std::copy(tp_.begin(), tp_.begin() + (long)(zb - za), zp_.begin() + (long)za);
+        std::copy(ti_.begin(), ti_.begin() + (long)(zb - za), id_.begin() + (long)za);
+    }
+
+    void dense_segment(int64_t f, int64_t l, int depth, size_t za, size_t zb) {
+        materialise(f, l, za, zb);
+#if defined(SIFT_ORDER_REPLAY_LIBSTDCXX_DENSE)
+        std::__introsort_loop(seg_.begin(), seg_.end(), (long)depth, __gnu_cxx::__ops::__iter_comp_iter(word_less));
+#else
+        dense_introsort(seg_.data(), seg_.data() + seg_.size(), depth, zb - za);
+#endif
+        collect(f, l, za, zb);
     }
 
     // libstdc++'s __introsort_loop for this comparator (key = bit 31; comp(a, b) = key(a) < key(b)), written out:
     // __move_median_to_first(first, first + 1, mid, last - 1), __unguarded_partition(first + 1, last, first), recursion on the
-    // right part, iteration on the left, 16-element threshold, heap sort when the depth budget is used up.
-    static void dense_introsort(uint32_t* first, uint32_t* last, int depth) {
+    // right part, iteration on the left, 16-element threshold, heap sort when the depth budget is used up.  `zeros` = unfiltered
+    // elements in the segment: a segment without any is left alone (nothing that happens to it can be observed).
+    //
+    // The two partition loops are restated without data-dependent branches.  With a filtered pivot `lo` stops at every filtered
+    // element and `hi` steps down by one per round, so round t swaps the t-th filtered element from the left with position
+    // last-t; with an unfiltered pivot `lo` steps up by one per round and `hi` jumps from one unfiltered element to the next
+    // lower one, so round t swaps position first+t with the t-th unfiltered element from the right.  Either way the positions
+    // the scanning pointer stops at are listed block by block with a branch-free compaction, and the swap loop has one
+    // (predictable) exit test.  Reading a block's contents before the swaps of that block is safe: the swaps only write behind
+    // the scanning pointer or beyond the other pointer, where the pointers have crossed by the time the scan gets there.
+    static void dense_introsort(uint32_t* first, uint32_t* last, int depth, size_t zeros) {
+        constexpr int kBlock = 64;
+        uint32_t* stops[kBlock + 1];
         while (last - first > 16) {
+            if (zeros == 0) return;
             if (depth == 0) {
-                std::partial_sort(first, last, last, [](uint32_t a, uint32_t b) { return !(a >> 31) && (b >> 31); });
+                std::partial_sort(first, last, last, word_less);
                 return;
             }
             --depth;
@@ -132,28 +151,61 @@ class SparseFilterSort {
                 else pick = b;
                 std::swap(*first, *pick);
             }
-            uint32_t *lo = first + 1, *hi = last;
-            if (*first >> 31) {
-                // pivot filtered: `lo` runs over unfiltered elements and stops at every filtered one, `hi` steps down by one
-                for (;;) {
-                    while (!(*lo >> 31)) ++lo;
-                    --hi;
-                    if (!(lo < hi)) break;
-                    std::swap(*lo, *hi);
-                    ++lo;
+            uint32_t* cut = nullptr;
+            if (zeros == (size_t)(last - first)) {
+                // nothing but unfiltered elements (the pivot is `mid`): neither pointer ever skips, round t swaps first+t with
+                // last-t until they meet — [first+1, last) is reversed, and both halves go on being shuffled like this
+                uint32_t *lo = first + 1, *hi = last - 1;
+                for (; lo < hi; ++lo, --hi) std::swap(*lo, *hi);
+                cut = lo;
+                const size_t left = (size_t)(cut - first);
+                dense_introsort(cut, last, depth, zeros - left);
+                last = cut;
+                zeros = left;
+            } else if (*first >> 31) {
+                // pivot filtered.  hi_prev = last - (t - 1); positions >= hi_prev hold filtered elements from round 2 on.
+                uint32_t* hi_prev = last;
+                uint32_t* blk = first + 1;
+                while (!cut) {
+                    if (blk >= hi_prev) { cut = hi_prev; break; }  // nothing filtered left below hi_prev: lo runs into it
+                    uint32_t* be = blk + kBlock < last ? blk + kBlock : last;
+                    int k = 0;
+                    for (uint32_t* q = blk; q < be; ++q) { stops[k] = q; k += (int)(*q >> 31); }
+                    for (int j = 0; j < k; ++j) {
+                        uint32_t* lo = stops[j] < hi_prev ? stops[j] : hi_prev;
+                        uint32_t* hi = hi_prev - 1;
+                        if (!(lo < hi)) { cut = lo; break; }
+                        std::swap(*lo, *hi);
+                        hi_prev = hi;
+                    }
+                    blk = be;
                 }
+                // [cut, last) holds filtered elements only
+                last = cut;
             } else {
-                // pivot unfiltered: `lo` never skips, `hi` skips filtered elements
-                for (;;) {
-                    --hi;
-                    while (*hi >> 31) --hi;
-                    if (!(lo < hi)) break;
-                    std::swap(*lo, *hi);
-                    ++lo;
+                // pivot unfiltered.  lo_prev = first + (t - 1); positions <= lo_prev hold unfiltered elements.
+                uint32_t* lo_prev = first;
+                uint32_t* blk = last;  // the block below `blk` is listed next
+                while (!cut) {
+                    if (blk <= lo_prev + 1) { cut = lo_prev + 1; break; }  // hi runs down into the unfiltered prefix
+                    uint32_t* bs = (blk - first) > kBlock ? blk - kBlock : first + 1;
+                    int k = 0;
+                    for (uint32_t* q = blk - 1; q >= bs; --q) { stops[k] = q; k += (int)((*q >> 31) ^ 1u); }
+                    for (int j = 0; j < k; ++j) {
+                        uint32_t* lo = lo_prev + 1;
+                        uint32_t* hi = stops[j] > lo_prev ? stops[j] : lo_prev;
+                        if (!(lo < hi)) { cut = lo; break; }
+                        std::swap(*lo, *hi);
+                        lo_prev = lo;
+                    }
+                    blk = bs;
                 }
+                // [first, cut) holds unfiltered elements only
+                const size_t left = (size_t)(cut - first);
+                dense_introsort(cut, last, depth, zeros - left);
+                last = cut;
+                zeros = left;
             }
-            dense_introsort(lo, last, depth);
-            last = lo;
         }
     }
 
@@ -223,25 +275,30 @@ class SparseFilterSort {
         int64_t top = m;  // Z[top, m) move
         while (top > 0 && (int64_t)Z[top - 1] >= l - T + 1) --top;
         if (top < m) {
-            // Merge the untouched bottom of the slice with the dropped elements (both ascending), ids riding along.  Everything
-            // below the first destination keeps its place in the arrays: after a few levels that is a dense prefix holding
-            // most of the unfiltered elements, so the work per level shrinks with the part that is still sparse.
-            int64_t ip = std::min<int64_t>(below(l - (int64_t)Z[m - 1]), top);
-            const int64_t x0 = ip;
+            // Merge the untouched bottom of the slice (ascending; element i goes before the dropped element of round t iff fewer
+            // than t filtered elements precede it) with the dropped elements (descending position = ascending t = ascending
+            // destination f + t + #bottom elements before it), ids riding along.  Everything below the first destination keeps
+            // its place.  The loop selects instead of branching: which side comes next is a coin flip.
+            const int64_t x0 = std::min<int64_t>(below(l - (int64_t)Z[m - 1]), top);
             tp_.resize((size_t)(m - x0));
             ti_.resize((size_t)(m - x0));
-            int64_t x = x0, o = 0;
-            for (int64_t i = m - 1; i >= top; --i) {  // descending position = ascending t = ascending destination
-                const int64_t p = Z[i], t = l - p;
-                while (ip < top && (int64_t)Z[ip] - (f + 1) - ip < t) ++ip;
-                for (; x < ip; ++x, ++o) { tp_[(size_t)o] = Z[x]; ti_[(size_t)o] = I[x]; }
-                tp_[(size_t)o] = (uint32_t)(f + t + ip);
-                ti_[(size_t)o] = I[i];
+            uint32_t* TP = tp_.data();
+            uint32_t* TI = ti_.data();
+            const int64_t base = f + 1;
+            int64_t ia = x0, ib = m - 1, o = 0;
+            while (ia < top && ib >= top) {
+                const int64_t za_ = Z[ia], t = l - (int64_t)Z[ib];
+                const bool stay_first = (za_ - base - ia) < t;
+                TP[o] = stay_first ? (uint32_t)za_ : (uint32_t)(f + t + ia);
+                TI[o] = stay_first ? I[ia] : I[ib];
                 ++o;
+                ia += stay_first ? 1 : 0;
+                ib -= stay_first ? 0 : 1;
             }
-            for (; x < top; ++x, ++o) { tp_[(size_t)o] = Z[x]; ti_[(size_t)o] = I[x]; }
-            std::copy(tp_.begin(), tp_.begin() + (long)(m - x0), Z + x0);
-            std::copy(ti_.begin(), ti_.begin() + (long)(m - x0), I + x0);
+            for (; ia < top; ++ia, ++o) { TP[o] = Z[ia]; TI[o] = I[ia]; }
+            for (; ib >= top; --ib, ++o) { TP[o] = (uint32_t)(f + (l - (int64_t)Z[ib]) + top); TI[o] = I[ib]; }
+            std::copy(TP, TP + (m - x0), Z + x0);
+            std::copy(TI, TI + (m - x0), I + x0);
         }
         return cut;
     }

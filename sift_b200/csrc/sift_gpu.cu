@@ -744,24 +744,29 @@ static int run_pyramid(sift_gpu_ctx* c, Slot& S, const Plan* p, const PlanSlot& 
     return 0;
 }
 
-// `zero_pos`: ascending positions of the unfiltered elements of an n-element vector.  Returns the kept elements, as
-// indices into zero_pos, in their post-sort order.  The std::sort permutation is replayed by SparseFilterSort
-// (order_replay.h); the canonical mode keeps the original order (what a stable partition would do).
-static void cleanup_order(uint32_t n, const std::vector<uint32_t>& zero_pos, bool canonical, std::vector<uint32_t>* kept) {
-    static thread_local SparseFilterSort sorter;
+// The reference's cleanup (sift.cpp:37-42) of an n-element vector whose unfiltered elements sit at the ascending positions
+// zero_pos[0, m): returns the kept elements, as indices into zero_pos, in their post-sort order (valid until the sorter's next
+// run).  The std::sort permutation is replayed by SparseFilterSort (order_replay.h); the canonical mode keeps the original
+// order (what a stable partition would do).  *kept_n = (uint16_t)m: the u16 size = distance(begin, first filtered) (sift.cpp:41).
+static const uint32_t* cleanup_order(SparseFilterSort& sorter, std::vector<uint32_t>& identity, uint32_t n, const uint32_t* zero_pos, size_t m,
+                                     bool canonical, size_t* kept_n) {
+    *kept_n = (size_t)(uint16_t)m;
     if (canonical) {
-        kept->resize(zero_pos.size());
-        for (size_t i = 0; i < zero_pos.size(); ++i) (*kept)[i] = (uint32_t)i;
-    } else {
-        *kept = sorter.run(n, zero_pos);
+        const size_t have = identity.size();
+        if (have < m) {
+            identity.resize(m);
+            for (size_t i = have; i < m; ++i) identity[i] = (uint32_t)i;
+        }
+        return identity.data();
     }
-    kept->resize((uint16_t)zero_pos.size());  // u16_t size = distance(begin, first filtered) (sift.cpp:41)
+    return sorter.run(n, zero_pos, m).data();
 }
 
 static std::atomic<long> g_rep_ns[6];  // SIFT_GPU_TRACE: CPU time inside replay_image by phase (summed over worker threads)
+static const bool g_rep_trace = getenv("SIFT_GPU_TRACE") != nullptr || getenv("SIFT_GPU_REPLAY_REPS") != nullptr;
 
 // Fills the result record of a point that reached _createDecriptors; returns whether it gets a descriptor.
-static bool make_keypoint(const sift_gpu_ctx* c, const Plan* p, const Surv& s, sift_gpu_keypoint* k, KeyIn* ki) {
+static inline bool make_keypoint(const sift_gpu_ctx* c, const Plan* p, const Surv& s, sift_gpu_keypoint* k, KeyIn* ki) {
     const int slot = p->class_target[(size_t)(s.octave * c->D + s.index)];
     const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
     k->x = s.x; k->y = s.y; k->octave = s.octave; k->index = s.index;
@@ -776,65 +781,84 @@ static bool make_keypoint(const sift_gpu_ctx* c, const Plan* p, const Surv& s, s
     return !reject;
 }
 
-// Host half of Sift::calculate between _eliminateEdgeResponses and _createDecriptors (sift.cpp:37-55).
-static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, const Surv* surv_in, uint32_t n_surv,
-                         ReplayOut* out) {
+// Host half of Sift::calculate between _eliminateEdgeResponses and _createDecriptors (sift.cpp:37-55).  Runs once per image on
+// the worker pool; `out` is reused from pass to pass (every field is rewritten here, the vectors keep their capacity) and the
+// scratch arrays are per thread, so the steady state allocates nothing.
+static void replay_image(const sift_gpu_ctx* c, const Plan* p, uint32_t n_cand, const Surv* S, uint32_t n_surv, ReplayOut* out) {
     const bool canonical = (c->prm.flags & SIFT_GPU_FLAG_ORDER_CANONICAL) != 0;
+    const bool strict = (c->prm.flags & SIFT_GPU_FLAG_STRICT) != 0;
     const int D = c->D;
-    auto tick = [] { return std::chrono::steady_clock::now(); };
-    auto lap = [](int i, std::chrono::steady_clock::time_point& t) {
+    static thread_local SparseFilterSort sorter;
+    static thread_local std::vector<uint32_t> zero_pos, identity;
+    std::chrono::steady_clock::time_point t_ph;
+    if (g_rep_trace) t_ph = std::chrono::steady_clock::now();
+    auto lap = [&](int i) {
+        if (!g_rep_trace) return;
         const auto n = std::chrono::steady_clock::now();
-        g_rep_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count();
-        t = n;
+        g_rep_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(n - t_ph).count();
+        t_ph = n;
     };
-    auto t_ph = tick();
-    // the device compacts survivors in canonical order (survivors_count / offsets / write kernels, eliminate.cu): `canon` ascends
-    const Surv* S = surv_in;
-    lap(0, t_ph);
-    // first cleanup over all candidates
-    std::vector<uint32_t> L1;  // survivor slots in vector order
-    {
-        std::vector<uint32_t> zero_pos(n_surv);
-        for (uint32_t s = 0; s < n_surv; ++s) zero_pos[s] = S[s].canon;
-        cleanup_order(n_cand, zero_pos, canonical, &L1);
+    out->status = SIFT_GPU_OK;
+    out->truncated = false;
+    // first cleanup over all candidates: the device compacts survivors in canonical order (survivors_count / offsets / write
+    // kernels, eliminate.cu), so `canon` ascends
+    zero_pos.resize(n_surv);
+    for (uint32_t s = 0; s < n_surv; ++s) zero_pos[s] = S[s].canon;
+    size_t n1 = 0;
+    const uint32_t* L1 = cleanup_order(sorter, identity, n_cand, zero_pos.data(), n_surv, canonical, &n1);  // survivor slots in vector order
+    out->n_survivors = (uint32_t)n1;
+    out->l1.resize(n1);
+    Surv* l1 = out->l1.data();
+    for (size_t i = 0; i < n1; ++i) l1[i] = S[L1[i]];
+    lap(1);
+    // _orientationAssignment bounds test (sift.cpp:173-178) and the dead blur's precondition (sift.cpp:184); both depend on the
+    // point's class (octave, index) only through two limits and one flag
+    int lim_x[kMaxOctaves * kMaxGauss], lim_y[kMaxOctaves * kMaxGauss];
+    bool throws[kMaxOctaves * kMaxGauss];
+    for (int cls = 0; cls < c->O * D; ++cls) {
+        const int slot = p->class_target[(size_t)cls];
+        lim_x[cls] = slot < 0 ? 0 : p->target_w[(size_t)slot] - kRegion;
+        lim_y[cls] = slot < 0 ? 0 : p->target_h[(size_t)slot] - kRegion;
+        throws[cls] = strict && 2 * kRegion < c->dead_blur_r[cls / D][cls % D] + 1;
     }
-    out->n_survivors = (uint32_t)L1.size();
-    lap(1, t_ph);
-    // _orientationAssignment bounds test (sift.cpp:173-178) and the dead blur's precondition (sift.cpp:184)
-    std::vector<uint32_t> inside;  // positions in L1 that pass the bounds test
-    for (size_t i = 0; i < L1.size(); ++i) {
-        const Surv& s = S[L1[i]];
-        const int slot = p->class_target[(size_t)(s.octave * D + s.index)];
-        const int tw = p->target_w[(size_t)slot], th = p->target_h[(size_t)slot];
-        const bool outside = (s.x < kRegion || s.x >= tw - kRegion) || (s.y < kRegion || s.y >= th - kRegion);
-        if (!outside) inside.push_back((uint32_t)i);
-        if (!outside && (c->prm.flags & SIFT_GPU_FLAG_STRICT) && 2 * kRegion < c->dead_blur_r[s.octave][s.index] + 1) {
-            out->status = SIFT_GPU_E_PRECONDITION;
-            return;
-        }
+    out->inside.resize(n1 + 1);  // positions in l1 that pass the bounds test (compacted without branching: one slot of slack)
+    uint32_t* inside = out->inside.data();
+    size_t n_in = 0;
+    bool thrown = false;
+    for (size_t i = 0; i < n1; ++i) {
+        const Surv& s = l1[i];
+        const int cls = s.octave * D + s.index;
+        const bool in = !((s.x < kRegion || s.x >= lim_x[cls]) || (s.y < kRegion || s.y >= lim_y[cls]));
+        inside[n_in] = (uint32_t)i;
+        n_in += in ? 1 : 0;
+        thrown |= in && throws[cls];
     }
-    lap(2, t_ph);
-    std::vector<uint32_t> L2;  // indices into `inside`
-    cleanup_order((uint32_t)L1.size(), inside, canonical, &L2);
-    lap(3, t_ph);
-    out->truncated = L2.size() != inside.size();
-    out->l1.resize(L1.size());
-    for (size_t i = 0; i < L1.size(); ++i) out->l1[i] = S[L1[i]];
-    out->kps.resize(L2.size());
-    out->key_of.assign(L2.size(), ~0u);
-    out->kp_l1.resize(L2.size());
-    out->keys.clear();
-    out->keys.reserve(L2.size());
-    for (size_t i = 0; i < L2.size(); ++i) {
-        out->kp_l1[i] = inside[L2[i]];
-        KeyIn ki;
-        if (make_keypoint(c, p, out->l1[inside[L2[i]]], &out->kps[i], &ki)) {
-            out->key_of[i] = (uint32_t)out->keys.size();
-            out->keys.push_back(ki);
-        }
+    out->inside.resize(n_in);
+    if (thrown) {
+        out->status = SIFT_GPU_E_PRECONDITION;
+        return;
     }
-    out->inside.swap(inside);
-    lap(4, t_ph);
+    lap(2);
+    size_t n2 = 0;
+    const uint32_t* L2 = cleanup_order(sorter, identity, (uint32_t)n1, inside, n_in, canonical, &n2);  // indices into `inside`
+    lap(3);
+    out->truncated = n2 != n_in;
+    out->kps.resize(n2);
+    out->key_of.resize(n2);
+    out->kp_l1.resize(n2);
+    out->keys.resize(n2);
+    sift_gpu_keypoint* kps = out->kps.data();
+    KeyIn* keys = out->keys.data();
+    size_t n_keys = 0;
+    for (size_t i = 0; i < n2; ++i) {
+        const uint32_t q = inside[L2[i]];
+        out->kp_l1[i] = q;
+        const bool has = make_keypoint(c, p, l1[q], &kps[i], &keys[n_keys]);
+        out->key_of[i] = has ? (uint32_t)n_keys : ~0u;
+        n_keys += has ? 1 : 0;
+    }
+    out->keys.resize(n_keys);
+    lap(4);
 }
 
 static double g_trace[8];  // SIFT_GPU_TRACE: host wall time per phase of the pass loop (diagnostics only)
@@ -958,7 +982,7 @@ static int begin_replay(sift_gpu_ctx* c, Slot& S) {
     if (overflow) CTX_CUDA(cudaStreamSynchronize(s));
 
     S.t_replay0 = now_ms();
-    S.rep.assign((size_t)nb, ReplayOut());
+    S.rep.resize((size_t)nb);  // the records (and their vectors' capacity) are reused from pass to pass; replay_image rewrites every field
     Slot* Sp = &S;
     c->pool->begin(nb, [c, p, Sp](int b) {
         const uint32_t n = Sp->h_n_surv[b];
@@ -1105,13 +1129,15 @@ static int redo_with_extra_orientations(sift_gpu_ctx* c, Slot& S, int slot_index
                 V.push_back(Entry{q, peaks[k * 36 + j]});
             }
         }
-        std::vector<uint32_t> kept;
-        cleanup_order((uint32_t)V.size(), zero_pos, canonical, &kept);
+        SparseFilterSort sorter;
+        std::vector<uint32_t> identity;
+        size_t n_kept = 0;
+        const uint32_t* kept = cleanup_order(sorter, identity, (uint32_t)V.size(), zero_pos.data(), zero_pos.size(), canonical, &n_kept);
         ReplayOut nr;
         nr.n_survivors = ro.n_survivors;
-        nr.kps.resize(kept.size());
-        nr.key_of.assign(kept.size(), ~0u);
-        for (size_t i = 0; i < kept.size(); ++i) {
+        nr.kps.resize(n_kept);
+        nr.key_of.assign(n_kept, ~0u);
+        for (size_t i = 0; i < n_kept; ++i) {
             const Entry& e = V[zero_pos[kept[i]]];
             KeyIn ki;
             if (make_keypoint(c, p, ro.l1[e.l1], &nr.kps[i], &ki)) {
@@ -1334,8 +1360,7 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
     c->error.clear();
     c->tm = sift_gpu_timings{};
     c->desc_blocks_used = 0;
-    c->outs.clear();
-    c->outs.resize((size_t)n_images);
+    if (c->outs.size() < (size_t)n_images) c->outs.resize((size_t)n_images);  // keypoint vectors keep their capacity from call to call
     int first_error = SIFT_GPU_OK;
     // Whatever way this call is left — a CUDA error in the middle of the pipelined loop included — no replay job may keep
     // running on the worker pool and no slot may keep device work queued on buffers the next call reuses.
@@ -1698,6 +1723,15 @@ int sift_gpu_debug_host_replay(const sift_gpu_params* params, int width, int hei
     }
     ReplayOut out;
     replay_image(c.get(), p.get(), n_candidates, surv.data(), n_unfiltered, &out);
+    if (const char* e = getenv("SIFT_GPU_REPLAY_REPS")) {  // development: CPU cost of the replay, per phase, buffers reused as in a slot
+        const int reps = atoi(e);
+        for (auto& a : g_rep_ns) a = 0;
+        const double t0 = now_ms();
+        for (int i = 0; i < reps; ++i) replay_image(c.get(), p.get(), n_candidates, surv.data(), n_unfiltered, &out);
+        const double us = (now_ms() - t0) * 1e3 / std::max(1, reps);
+        fprintf(stderr, "[sift_gpu replay cpu] %.1f us per image: sort1 %.1f  bounds %.1f  sort2 %.1f  keypoints %.1f\n", us,
+                g_rep_ns[1] * 1e-3 / reps, g_rep_ns[2] * 1e-3 / reps, g_rep_ns[3] * 1e-3 / reps, g_rep_ns[4] * 1e-3 / reps);
+    }
     if (n_survivors) *n_survivors = out.n_survivors;
     *n_kps = (uint32_t)out.kps.size();
     if (out.status != SIFT_GPU_OK) return out.status;

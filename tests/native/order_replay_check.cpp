@@ -1,5 +1,5 @@
-// Test helper (CPU): SparseFilterSort with its own dense introsort (the path taken where libstdc++'s internals are not
-// available, -DSIFT_ORDER_REPLAY_OWN_DENSE) against the real std::sort with the reference's comparator
+// Test helper (CPU): SparseFilterSort (own dense introsort by default; -DSIFT_ORDER_REPLAY_LIBSTDCXX_DENSE hands dense segments to
+// libstdc++'s internal loop instead) against the real std::sort with the reference's comparator
 // (interestpoint.hpp:57-62) over many sizes, densities and layouts.  Exit code 0 = every case agrees.
 #include <algorithm>
 #include <cstdint>

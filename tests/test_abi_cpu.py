@@ -331,7 +331,7 @@ def test_order_replay_portable_dense_sort(tmp_path):
     """order_replay.h hands dense segments to libstdc++'s own introsort loop; where that internal is not available it uses its
     own restatement of the algorithm.  Both builds must reproduce the real std::sort permutation (tests/native/order_replay_check.cpp)."""
     src = os.path.join(ROOT, "tests", "native", "order_replay_check.cpp")
-    for name, defs in (("lib", []), ("own", ["-DSIFT_ORDER_REPLAY_OWN_DENSE"])):
+    for name, defs in (("own", []), ("lib", ["-DSIFT_ORDER_REPLAY_LIBSTDCXX_DENSE"])):
         exe = str(tmp_path / f"orc_{name}")
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", *defs, "-o", exe, src])
         out = subprocess.run([exe], capture_output=True, text=True)
