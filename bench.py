@@ -292,7 +292,7 @@ def run_ours(args):
 
     def do_steps(base_ptr, memory, n_steps, first, dtype=capi.DTYPE_F32):
         acc = {"pyramid_ms": 0.0, "span_ms": 0.0, "launches": 0, "kps": 0, "cands": 0, "surv": 0, "device_total_ms": 0.0,
-               "host_order_ms": 0.0, "stages": {}}
+               "host_order_ms": 0.0, "stages": {}, "h2d_bytes": 0, "packed": 0}
         for s in range(n_steps):
             rc, res = g.run_raw(descs(base_ptr, memory, first + s, dtype), B)
             if rc != 0:
@@ -300,6 +300,7 @@ def run_ours(args):
             t = g.timings()
             acc["pyramid_ms"] += t["pyramid_ms"]; acc["span_ms"] += t["span_ms"]; acc["launches"] += int(t["kernel_launches"])
             acc["device_total_ms"] += t["device_total_ms"]; acc["host_order_ms"] += t["host_order_ms"]
+            acc["h2d_bytes"] += int(t["h2d_bytes"]); acc["packed"] += int(t["packed_images"])
             for k2, v in t.items():
                 if k2.endswith("_ms"):
                     acc["stages"][k2] = acc["stages"].get(k2, 0.0) + v
@@ -327,8 +328,35 @@ def run_ours(args):
         clocks = sampler.stop() if sampler else None
         return wall, acc, clocks
 
+    if args.quick_e2e:
+        # development: only the end-to-end leg, with and without the packed upload (SIFT_GPU_HOST_PACK), one line
+        out = {}
+        for mode in ("default", "0", "1"):
+            if mode == "default":
+                os.environ.pop("SIFT_GPU_HOST_PACK", None)
+            else:
+                os.environ["SIFT_GPU_HOST_PACK"] = mode
+            w, a, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
+            out["pack_" + mode] = {"images_per_s": args.steps * B / w, "h2d_bytes_per_step": a["h2d_bytes"] // args.steps,
+                                   "packed_images_per_step": a["packed"] // args.steps, "host_order_ms_per_image": a["host_order_ms"] / (args.steps * B)}
+        os.environ.pop("SIFT_GPU_HOST_PACK", None)
+        w, a, _ = timed(dev_frames.data_ptr(), capi.MEM_DEVICE)
+        out["value"] = {"images_per_s": args.steps * B / w, "host_order_ms_per_image": a["host_order_ms"] / (args.steps * B)}
+        out["host_cpus"] = len(os.sched_getaffinity(0))
+        print(json.dumps({"quick_e2e": out}), flush=True)
+        g.close()
+        return
+
     wall_d, acc_d, clocks = timed(dev_frames.data_ptr(), capi.MEM_DEVICE)
+    # end to end: pinned host f32 frames through the C-ABI call.  The library packs 8-bit-valued f32 frames to bytes on its host
+    # threads inside the call (lossless, include/sift_gpu.h) where its policy allows; the bytes that travelled are its own count.
     wall_h, acc_h, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
+    wall_f32, acc_f32 = wall_h, acc_h
+    if acc_h["packed"]:
+        # supplementary: the same call with the packing switched off (every frame travels as 4 bytes per pixel)
+        os.environ["SIFT_GPU_HOST_PACK"] = "0"
+        wall_f32, acc_f32, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
+        os.environ.pop("SIFT_GPU_HOST_PACK", None)
     # supplementary: the same frames as 8-bit pixels (what a decoder produces before Vigra's importImage widens them,
     # main.cpp:52-54); the library widens on the device, results are identical, the upload is 4x smaller
     host_u8 = host_frames.to(torch.uint8).pin_memory()
@@ -366,14 +394,14 @@ def run_ours(args):
 
     # run() is synchronous (it returns after its last stream sync), so the host clock around the K steps equals the
     # device-side span; span_ms (CUDA events on the library's stream) is reported beside it.  Max over ranks.
-    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_r["pyramid_ms"], wall_u8, acc_o["pyramid_ms"]],
+    (mx, sm) = shard.reduce_max_sum(dist, dev, [wall_d, wall_h, acc_d["span_ms"], acc_r["pyramid_ms"], wall_u8, acc_o["pyramid_ms"], wall_f32],
                                     [args.steps * B, acc_d["launches"], acc_d["kps"], acc_d["cands"]])
     if rank != 0:
         g.close()
         dist.barrier()
         dist.destroy_process_group()
         return
-    wall_d, wall_h, span_d, pyr_ms, wall_u8, pyr_other_ms = mx
+    wall_d, wall_h, span_d, pyr_ms, wall_u8, pyr_other_ms, wall_f32 = mx
     images, launches, kps, cands = sm
     value = images / wall_d
     e2e = images / wall_h
@@ -404,8 +432,14 @@ def run_ours(args):
                    "keypoints_per_image": kps / images, "candidates_per_image": cands / images,
                    "host_cpus": len(os.sched_getaffinity(0)), "bound_to_gpu_numa_cpus": numa},
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * per_img_h2d, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * wall_h / args.steps},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(acc_h["h2d_bytes"] // max(1, args.steps)), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * wall_h / args.steps, "host_buffers": "pinned f32 frames, %d bytes each" % per_img_h2d,
+                "upload": ("%d of %d frames per step were 8-bit valued and travelled as bytes: packed by the library's host threads inside the timed call, "
+                           "widened on the device, results bit-identical (include/sift_gpu.h, tests/test_gpu_host_pack.py)" % (acc_h["packed"] // max(1, args.steps), B))
+                          if acc_h["packed"] else "f32 frames as they are (packing off: fewer than 8 host threads for this context, or SIFT_GPU_HOST_PACK=0)"},
+        "e2e_f32_upload": {"value": images / wall_f32, "unit": "images/s", "h2d_bytes_per_step": int(acc_f32["h2d_bytes"] // max(1, args.steps)),
+                           "ms_per_step": 1e3 * wall_f32 / args.steps,
+                           "note": "supplementary: the same call with SIFT_GPU_HOST_PACK=0, every frame uploaded as 4 bytes per pixel (PCIe-bound)"},
         "e2e_u8_input": {"value": images / wall_u8, "unit": "images/s", "h2d_bytes_per_step": B * W * H, "ms_per_step": 1e3 * wall_u8 / args.steps,
                          "note": "supplementary: same call with SIFT_GPU_DTYPE_U8 host frames (identical results)"},
         "gpu_launches": int(launches),
@@ -448,6 +482,7 @@ def main():
     ap.add_argument("--device-batch", type=int, default=192, help="frames per device pass (ctx max_batch); several passes are in flight")
     ap.add_argument("--flags", type=int, default=0, help="SIFT_GPU_FLAG_* bits (1 canonical order, 4 FMA blur)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick-e2e", action="store_true", help="development: only the end-to-end leg with the packed upload off / on")
     ap.add_argument("--no-configs", action="store_true", help="skip the single-image measurements of BASELINE configs 1, 2, 4")
     ap.add_argument("--literal-1500", action="store_true", help="only time the literal reference CPU path on a 1500x1500 frame (minutes)")
     args = ap.parse_args()

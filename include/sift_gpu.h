@@ -106,13 +106,20 @@ typedef struct sift_gpu_timings {
     float span_ms;         /* CUDA-event time from the first enqueue to the last completion of every device pass
                               (includes the host order replay that sits between the two device halves) */
     uint64_t kernel_launches;
+    uint64_t h2d_bytes;      /* frame bytes uploaded from host memory, as they travelled (a packed frame counts 1 byte per pixel) */
+    uint32_t packed_images;  /* host f32 frames that were 8-bit valued and went up as bytes (lossless; see sift_gpu_run) */
+    uint32_t reserved;
 } sift_gpu_timings;
 
 typedef struct sift_gpu_ctx sift_gpu_ctx;
 
 /* Replaces: Sift::Sift(...) (sift.hpp:66-71). */
 int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out);
-/* Replaces: Sift::calculate (sift.cpp:19-57) for n_images independent images. */
+/* Replaces: Sift::calculate (sift.cpp:19-57) for n_images independent images.
+ * Host f32 frames whose pixels are all exact 8-bit values (what vigra::importImage delivers, main.cpp:52-54) are packed to
+ * bytes by host threads while earlier passes run, uploaded as bytes and widened on the device — a quarter of the PCIe traffic,
+ * bit-identical results; any other frame makes its pass travel as f32.  Applies to passes of at least 8 images on contexts
+ * with at least 8 host threads (SIFT_GPU_HOST_THREADS); SIFT_GPU_HOST_PACK=0 / 1 in the environment forces it off / on. */
 int sift_gpu_run(sift_gpu_ctx* ctx, const sift_gpu_image* images, int n_images, sift_gpu_result* results);
 void sift_gpu_destroy(sift_gpu_ctx* ctx);
 const char* sift_gpu_last_error(const sift_gpu_ctx* ctx); /* ctx may be NULL: last create() error */
@@ -151,6 +158,11 @@ int sift_gpu_debug_host_replay(const sift_gpu_params* params, int width, int hei
                                const uint16_t* xs, const uint16_t* ys, const uint8_t* octave, const uint8_t* index,
                                uint32_t n_unfiltered, sift_gpu_keypoint* kps, uint32_t capacity, uint32_t* n_kps,
                                uint32_t* n_survivors);
+/* The lossless f32 -> u8 packing sift_gpu_run applies to host frames ahead of their upload (see sift_gpu_run): packs `rows` rows
+ * of `w` floats (row stride in bytes) into bytes (row pitch dst_pitch).  Returns 1 when every pixel is an exact 8-bit value (an
+ * integer in [0, 255] whose float -> u8 -> float round trip is bit-identical: no fractions, negatives, -0.0f, NaN, Inf), else 0
+ * and dst is unspecified.  Host code, no device needed. */
+int sift_gpu_debug_pack_rows_u8(const float* src, size_t src_stride_bytes, int w, int rows, uint8_t* dst, size_t dst_pitch);
 /* The std::sort(cmpByFilter) permutation the host replays (sift.cpp:37): order[i] = source index. */
 int sift_gpu_debug_sort_order(const uint8_t* filtered, uint32_t n, uint32_t* order);
 /* The same permutation restricted to the unfiltered elements (all the pipeline needs), computed by the sparse

@@ -48,7 +48,8 @@ class Result(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "pyramid_ms", "extrema_ms", "eliminate_ms", "d2h_survivors_ms",
                                          "host_order_ms", "h2d_keypoints_ms", "orientation_ms", "descriptor_ms",
-                                         "d2h_results_ms", "device_total_ms", "wall_ms", "span_ms")] + [("kernel_launches", C.c_uint64)]
+                                         "d2h_results_ms", "device_total_ms", "wall_ms", "span_ms")] + [
+                    ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("packed_images", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class SiftGpuError(RuntimeError):
@@ -106,6 +107,8 @@ def load():
     L.sift_gpu_debug_host_replay.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.sift_gpu_debug_pack_rows_u8.restype = C.c_int
+    L.sift_gpu_debug_pack_rows_u8.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     _lib = L
     return L
 
@@ -114,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "sift_gpu_create", "sift_gpu_run", "sift_gpu_destroy", "sift_gpu_last_error", "sift_gpu_get_timings",
     "sift_gpu_version", "sift_gpu_debug_get_level", "sift_gpu_debug_blur", "sift_gpu_debug_reduce",
     "sift_gpu_debug_increase", "sift_gpu_debug_extrema", "sift_gpu_debug_eliminate", "sift_gpu_debug_get_candidates",
-    "sift_gpu_debug_sort_order", "sift_gpu_debug_sort_order_fast", "sift_gpu_debug_host_replay",
+    "sift_gpu_debug_sort_order", "sift_gpu_debug_sort_order_fast", "sift_gpu_debug_host_replay", "sift_gpu_debug_pack_rows_u8",
 ]
 
 
@@ -158,6 +161,18 @@ def host_replay(width, height, n_candidates, canon, xs, ys, octave, index, *, do
     if rc != 0:
         raise SiftGpuError(rc, "host_replay")
     return kps[: n.value].copy(), ns.value
+
+
+def pack_u8(img, dst_pitch=None):
+    """The lossless f32 -> u8 frame packing of the upload path (pack_host.cpp).  Returns the bytes, or None when some pixel
+    is not an exact 8-bit value."""
+    img = np.asarray(img, np.float32)
+    assert img.ndim == 2 and img.strides[1] == 4
+    h, w = img.shape
+    pitch = dst_pitch or w
+    out = np.zeros((h, pitch), np.uint8)
+    ok = load().sift_gpu_debug_pack_rows_u8(img.ctypes.data, img.strides[0], w, h, out.ctypes.data, pitch)
+    return out[:, :w] if ok else None
 
 
 def results_to_dicts(res):

@@ -232,6 +232,11 @@ struct Slot {
     uint32_t *h_n_cand = nullptr, *h_n_surv = nullptr;  // pinned
     Surv* h_surv = nullptr;                              // pinned: B x kSurvFirst (speculative copy)
     std::vector<std::vector<Surv>> surv_overflow;        // per image, only when n_surv > kSurvFirst
+    // host f32 frames of the next pass packed to bytes (pack_host.cpp) while the current passes run
+    uint8_t* h_pack = nullptr;      // pinned, B x max_in_px, laid out like d_in_u8
+    bool pack_job = false;          // a packing job for this slot is on the pack pool
+    std::atomic<int> pack_bad{0};   // some pixel of the pass is not an exact 8-bit value: the pass travels as f32
+    bool packed = false;            // stage A uploads h_pack instead of the caller's frames
     // keypoint stage buffers (grow on demand)
     size_t key_cap = 0;
     KeyIn* d_keys = nullptr; KeyIn* h_keys = nullptr;
@@ -296,6 +301,8 @@ struct sift_gpu_ctx {
 
     std::map<std::pair<int, int>, Plan*> plans;
     Pool* pool = nullptr;
+    Pool* pack_pool = nullptr;   // second pool: packing the next pass's frames overlaps the order replay of an earlier one
+    int host_threads = 0;
 
     sift_gpu_timings tm{};
     cudaEvent_t ev_first = nullptr, ev_last = nullptr;
@@ -876,7 +883,19 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
     S.launches = 0;
     CTX_CUDA(cudaEventRecord(S.ev[0], s));
     // upload (main.cpp:52-54 leaves band 0 as float 0..255; u8 input is widened on the device)
-    for (int b = 0; b < nb;) {
+    if (S.packed) {
+        // the pass's f32 frames were packed to bytes on the host (pack_begin): same layout as d_in_u8, one transfer when dense
+        const size_t img_bytes = (size_t)p->in_pitch * (size_t)p->in_h;
+        if (img_bytes == c->max_in_px) {
+            CTX_CUDA(cudaMemcpyAsync(S.d_in_u8, S.h_pack, img_bytes * (size_t)nb, cudaMemcpyHostToDevice, s));
+        } else {
+            for (int b = 0; b < nb; ++b)
+                CTX_CUDA(cudaMemcpyAsync(S.d_in_u8 + (size_t)b * c->max_in_px, S.h_pack + (size_t)b * c->max_in_px, img_bytes, cudaMemcpyHostToDevice, s));
+        }
+        c->tm.h2d_bytes += img_bytes * (size_t)nb;
+        c->tm.packed_images += (uint32_t)nb;
+    }
+    for (int b = 0; b < nb && !S.packed;) {
         const sift_gpu_image& im = *S.imgs[(size_t)b].img;
         const size_t esz = im.dtype == SIFT_GPU_DTYPE_U8 ? 1 : 4;
         const size_t pitch = im.row_stride_bytes ? (size_t)im.row_stride_bytes : (size_t)im.width * esz;
@@ -892,9 +911,11 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
                        (const char*)S.imgs[(size_t)(b + n)].img->data == (const char*)im.data + (size_t)n * bytes)
                     ++n;
             CTX_CUDA(cudaMemcpyAsync(dst, im.data, bytes * (size_t)n, kind, s));
+            if (im.memory != SIFT_GPU_MEM_DEVICE) c->tm.h2d_bytes += bytes * (size_t)n;
             b += n;
         } else {
             CTX_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->in_pitch * esz, im.data, pitch, (size_t)im.width * esz, (size_t)im.height, kind, s));
+            if (im.memory != SIFT_GPU_MEM_DEVICE) c->tm.h2d_bytes += (size_t)im.width * esz * (size_t)im.height;
             ++b;
         }
     }
@@ -903,7 +924,7 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
     // pyramid streams, the stage-boundary events as external event-record nodes) and from then on one graph launch
     // replaces ~50 launch calls — less host time per pass and shorter gaps between the short kernels of the small octaves.
     static const bool graphs_on = [] { const char* e = getenv("SIFT_GPU_GRAPHS"); return !(e && atoi(e) == 0) && !getenv("SIFT_GPU_TRACE_PYR"); }();
-    const bool u8 = S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8;
+    const bool u8 = S.packed || S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8;
     Slot::StageGraph* G = graphs_on ? &S.graphs[std::make_tuple((const void*)p, nb, u8 ? 1 : 0)] : nullptr;
     if (G && G->exec) {
         CTX_CUDA(cudaGraphLaunch(G->exec, s));
@@ -1307,6 +1328,8 @@ int sift_gpu_create(const sift_gpu_params* params, sift_gpu_ctx** out) {
     // default: the host's hardware threads shared out over its GPUs (one process per GPU is the deployment), at most 16
     if (nthreads <= 0) nthreads = (int)std::min<unsigned>(16u, std::max(4u, std::thread::hardware_concurrency() / (unsigned)std::max(1, ndev)));
     c->pool = new Pool(nthreads - 1);
+    c->pack_pool = new Pool(nthreads - 1);
+    c->host_threads = nthreads;
     *out = c;
     return SIFT_GPU_OK;
 }
@@ -1317,6 +1340,7 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
     for (Slot& S : c->slots)
         if (S.stream) cudaStreamSynchronize(S.stream);
     delete c->pool;
+    delete c->pack_pool;
     for (auto& kv : c->plans) {
         Plan* p = kv.second;
         cudaFree(p->d_maps);
@@ -1331,7 +1355,7 @@ void sift_gpu_destroy(sift_gpu_ctx* c) {
         for (auto& kv : S.graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         S.graphs.clear();
         cudaFree(S.d_mask); cudaFree(S.d_col_count); cudaFree(S.d_col_off); cudaFree(S.d_cands); cudaFree(S.d_surv);
-        cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFree(S.d_slice); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv);
+        cudaFree(S.d_n_cand); cudaFree(S.d_n_surv); cudaFree(S.d_slice); cudaFreeHost(S.h_n_cand); cudaFreeHost(S.h_n_surv); cudaFreeHost(S.h_surv); cudaFreeHost(S.h_pack);
         cudaFree(S.d_keys); cudaFree(S.d_key_img); cudaFree(S.d_key_first); cudaFree(S.d_orient); cudaFree(S.d_npeaks);
         cudaFree(S.d_peaks); cudaFree(S.d_desc); cudaFree(S.d_grad); cudaFree(S.d_tables);
         cudaFree(S.grid.count); cudaFree(S.grid.offset); cudaFree(S.grid.cursor); cudaFree(S.grid.cell_keys);
@@ -1353,6 +1377,63 @@ struct PassPlan {
     std::vector<ChunkImage> imgs;
 };
 
+// ---- lossless f32 -> u8 packing of host frames ahead of their upload (pack_host.cpp) ------------------------------
+extern "C" int sift_gpu_debug_pack_rows_u8(const float* src, size_t src_stride_bytes, int w, int rows, uint8_t* dst, size_t dst_pitch);
+
+constexpr int kPackMinImages = 8;   // below this a pass is latency work: packing would only delay its upload
+constexpr int kPackRows = 128;      // rows per work item
+
+// Policy: SIFT_GPU_HOST_PACK=0 / 1 (read per run) turns it off / on; by default it is on when this context has at least 8
+// host threads to itself (a frame costs about a millisecond of one core: with fewer threads the order replay needs them more).
+static bool pack_enabled(const sift_gpu_ctx* c) {
+    if (const char* e = getenv("SIFT_GPU_HOST_PACK")) return atoi(e) != 0;
+    return c->host_threads >= 8;
+}
+
+// Starts packing the frames of pass `pp` into the slot's pinned staging buffer on the pack pool and returns; pack_end joins.
+// The slot's previous pass has been uploaded long ago (its stage A was waited for before its order replay began).
+static int pack_begin(sift_gpu_ctx* c, Slot& S, const PassPlan& pp) {
+    S.pack_job = false;
+    const int nb = (int)pp.imgs.size();
+    if (nb < kPackMinImages || !c->pack_pool) return 0;
+    for (const ChunkImage& ci : pp.imgs)
+        if (ci.img->dtype != SIFT_GPU_DTYPE_F32 || ci.img->memory != SIFT_GPU_MEM_HOST) return 0;
+    if (!S.h_pack) {
+        if (cudaHostAlloc((void**)&S.h_pack, c->max_in_px * (size_t)c->B, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            S.h_pack = nullptr;
+            return 0;  // no staging memory: the pass travels as f32
+        }
+    }
+    CTX_CUDA(cudaEventSynchronize(S.ev[5]));  // belt and braces: the last upload out of h_pack has completed
+    const Plan* p = pp.plan;
+    const int blocks = (p->in_h + kPackRows - 1) / kPackRows;
+    S.pack_bad.store(0);
+    S.pack_job = true;
+    Slot* Sp = &S;
+    const PassPlan* ppp = &pp;
+    const size_t img_stride = c->max_in_px;
+    c->pack_pool->begin(nb * blocks, [Sp, ppp, p, blocks, img_stride](int item) {
+        if (Sp->pack_bad.load(std::memory_order_relaxed)) return;
+        const int b = item / blocks, y0 = (item % blocks) * kPackRows;
+        const sift_gpu_image& im = *ppp->imgs[(size_t)b].img;
+        const size_t stride = im.row_stride_bytes ? (size_t)im.row_stride_bytes : (size_t)im.width * 4;
+        const int rows = std::min(kPackRows, p->in_h - y0);
+        const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(im.data) + (size_t)y0 * stride);
+        uint8_t* dst = Sp->h_pack + (size_t)b * img_stride + (size_t)y0 * (size_t)p->in_pitch;
+        if (!sift_gpu_debug_pack_rows_u8(src, stride, p->in_w, rows, dst, (size_t)p->in_pitch)) Sp->pack_bad.store(1, std::memory_order_relaxed);
+    });
+    return 0;
+}
+
+static void pack_end(sift_gpu_ctx* c, Slot& S) {
+    S.packed = false;
+    if (!S.pack_job) return;
+    c->pack_pool->end();
+    S.pack_job = false;
+    S.packed = S.pack_bad.load() == 0;
+}
+
 int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, sift_gpu_result* results) {
     if (!c || (n_images > 0 && (!images || !results)) || n_images < 0) return set_error(c, SIFT_GPU_E_INVALID, "null argument");
     const double t0 = now_ms();
@@ -1370,8 +1451,10 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
         ~Quiesce() {
             if (clean) return;
             if (c->pool) c->pool->end();
+            if (c->pack_pool) c->pack_pool->end();
             for (int si = 0; si < c->n_slots; ++si) {
                 Slot& S = c->slots[si];
+                S.pack_job = false;
                 if (S.stream) cudaStreamSynchronize(S.stream);
                 for (cudaStream_t a : S.aux)
                     if (a) cudaStreamSynchronize(a);
@@ -1436,17 +1519,28 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
             }
         return 0;
     };
+    const bool packing = pack_enabled(c);
+    // frames of pass k+1 are packed on the second pool while pass k's stage A is enqueued and an earlier pass is replayed;
+    // stage_a(k+1) joins that job before it uploads
+    auto pack_ahead = [&](int k) -> int {
+        if (packing && k >= 0 && k < np) CTX_TRY(pack_begin(c, c->slots[k % ns], passes[(size_t)k]));
+        return 0;
+    };
     auto stage_a = [&](int k) -> int {
         Slot& S = c->slots[k % ns];
         S.plan = passes[(size_t)k].plan;
         S.imgs = passes[(size_t)k].imgs;
         S.busy = true;
         if (k == 0) CTX_CUDA(cudaEventRecord(c->ev_first, S.stream));
+        const double t_p0 = now_ms();
+        pack_end(c, S);
+        g_trace[6] += now_ms() - t_p0;
         const double t_a0 = now_ms();
         CTX_TRY(enqueue_stage_a(c, S, k % ns));
         g_trace[0] += now_ms() - t_a0;
         return 0;
     };
+    CTX_TRY(pack_ahead(0));
     if (lag_b >= 1 && ns >= 3) {
         // Iteration k: the replay of pass k - lag_b runs on the worker pool while this thread collects pass k - ns (which
         // frees the slot) and enqueues stage A of pass k; then it joins the replay and enqueues that pass's stage B.
@@ -1457,6 +1551,7 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
             if (k - ns >= 0 && k - ns < np) CTX_TRY(collect(k - ns));
             if (k < np) CTX_TRY(stage_a(k));
             if (rb) CTX_TRY(end_replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
+            CTX_TRY(pack_ahead(k + 1));
         }
     } else {
         for (int k = 0; k < np + lag_f; ++k) {
@@ -1467,6 +1562,7 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
                 CTX_TRY(end_replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
             }
             if (k - lag_f >= 0 && k - lag_f < np) CTX_TRY(collect(k - lag_f));
+            CTX_TRY(pack_ahead(k + 1));
         }
     }
     if (np > 0) {
@@ -1479,8 +1575,8 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
                             c->tm.h2d_keypoints_ms + c->tm.orientation_ms + c->tm.descriptor_ms + c->tm.d2h_results_ms;
     c->tm.wall_ms = (float)(now_ms() - t0);
     if (getenv("SIFT_GPU_TRACE")) {
-        fprintf(stderr, "[sift_gpu trace] %d passes, wall %.2f ms: enqueueA %.2f  waitA %.2f  replay %.2f  enqueueB %.2f  waitC %.2f  collect %.2f\n", np,
-                c->tm.wall_ms, g_trace[0], g_trace[1], g_trace[2], g_trace[3], g_trace[4], g_trace[5]);
+        fprintf(stderr, "[sift_gpu trace] %d passes, wall %.2f ms: enqueueA %.2f  waitA %.2f  replay %.2f  enqueueB %.2f  waitC %.2f  collect %.2f  packjoin %.2f (%u frames packed)\n", np,
+                c->tm.wall_ms, g_trace[0], g_trace[1], g_trace[2], g_trace[3], g_trace[4], g_trace[5], g_trace[6], c->tm.packed_images);
     }
     if (getenv("SIFT_GPU_TRACE"))
         fprintf(stderr, "[sift_gpu replay cpu] per image: radix %.1f us  sort1 %.1f  bounds %.1f  sort2 %.1f  keypoints %.1f\n", g_rep_ns[0] * 1e-3 / std::max(1, n_images),

@@ -79,3 +79,35 @@ def test_host_replay_rejects_bad_lists():
         capi.host_replay(64, 64, 10, [1], [20], [20], [0], [0])
     got, ns = capi.host_replay(64, 64, 10, [], [], [], [], [])
     assert got.size == 0 and ns == 0
+
+
+# ---- the lossless f32 -> u8 packing of the upload path (sift_b200/csrc/pack_host.cpp) -----------------------------
+def test_frame_packing_accepts_exactly_the_8_bit_valued_frames():
+    from sift_b200.synth import synth_frame
+
+    img = synth_frame(333, 77, 4)
+    out = capi.pack_u8(img)
+    assert out is not None and np.array_equal(out, img.astype(np.uint8))
+    assert np.array_equal(out.astype(np.float32).view(np.uint32), img.view(np.uint32))      # the device widening restores every bit
+    for bad in (0.5, -1.0, 256.0, 255.00002, 1e9, float("nan"), float("inf"), -float("inf"), -0.0, 1e-30):
+        for pos in ((0, 0), (76, 332), (40, 161), (7, 17), (76, 320)):   # vector body, row tails, first and last pixel
+            t = img.copy()
+            t[pos] = bad
+            assert capi.pack_u8(t) is None, (bad, pos)
+    for v in (0.0, 255.0):
+        t = img.copy()
+        t[3, 5] = v
+        assert capi.pack_u8(t) is not None
+
+
+@pytest.mark.parametrize("w", [1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 211])
+def test_frame_packing_ragged_widths_strides_and_pitches(w):
+    a = np.random.default_rng(w).integers(0, 256, (13, w)).astype(np.float32)
+    o = capi.pack_u8(a, dst_pitch=((w + 31) // 32) * 32)
+    assert o is not None and np.array_equal(o, a.astype(np.uint8))
+    big = np.full((13, w + 5), 0.25, np.float32)     # a strided view: the padding columns hold non-packable values
+    big[:, :w] = a
+    o = capi.pack_u8(big[:, :w])
+    assert o is not None and np.array_equal(o, a.astype(np.uint8))
+    big[6, w - 1] = 7.5
+    assert capi.pack_u8(big[:, :w]) is None
