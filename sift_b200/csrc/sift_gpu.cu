@@ -25,6 +25,7 @@
 #include "../../include/sift_gpu.h"
 #include "common.cuh"
 #include "order_replay.h"
+#include "pool.h"
 #include "tma.cuh"
 
 namespace siftgpu {
@@ -73,78 +74,6 @@ static std::vector<int> resize_index_map(int n_old, int n_new) {
     for (int i = 0; i < n_new; ++i, x += dx) m[(size_t)i] = (int)x;
     return m;
 }
-
-// ---- tiny worker pool for the per-image order replay ------------------------------------------------
-class Pool {
-   public:
-    explicit Pool(int n) {
-        for (int i = 0; i < n; ++i) workers.emplace_back([this] { loop(); });
-    }
-    ~Pool() {
-        { std::lock_guard<std::mutex> g(m); stop = true; }
-        cv.notify_all();
-        for (auto& t : workers) t.join();
-    }
-    // begin() hands fn(0..n-1) to the workers and returns; end() lets the caller take what is left and waits for the rest.
-    void begin(int n, std::function<void(int)> fn) {
-        held = std::move(fn);
-        held_n = n;
-        if (n <= 0 || workers.empty()) return;
-        {
-            // total and pending first, the item counter last: a worker still in the item loop of the previous job that draws
-            // an index after the reset must already see this job's bounds
-            std::lock_guard<std::mutex> g(m);
-            job = &held; total.store(n); pending.store(n); next.store(0);
-        }
-        cv.notify_all();
-    }
-    void end() {
-        const int n = held_n;
-        held_n = 0;
-        if (n <= 0) return;
-        if (workers.empty()) { for (int i = 0; i < n; ++i) held(i); return; }
-        for (;;) {
-            int i = next.fetch_add(1);
-            if (i >= n) break;
-            held(i);
-            if (pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m); done_cv.notify_all(); }
-        }
-        std::unique_lock<std::mutex> lk(m);
-        done_cv.wait(lk, [this] { return pending.load() == 0; });
-        job = nullptr;
-    }
-    void parallel_for(int n, const std::function<void(int)>& fn) {
-        begin(n, fn);
-        end();
-    }
-
-   private:
-    void loop() {
-        for (;;) {
-            const std::function<void(int)>* j;
-            {
-                std::unique_lock<std::mutex> lk(m);
-                cv.wait(lk, [this] { return stop || (job && next.load() < total.load()); });
-                if (stop) return;
-                j = job;
-            }
-            for (;;) {
-                int i = next.fetch_add(1);
-                if (i >= total.load()) break;
-                (*j)(i);
-                if (pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m); done_cv.notify_all(); }
-            }
-        }
-    }
-    std::vector<std::thread> workers;
-    std::mutex m;
-    std::condition_variable cv, done_cv;
-    const std::function<void(int)>* job = nullptr;
-    std::function<void(int)> held;
-    int held_n = 0;
-    std::atomic<int> next{0}, pending{0}, total{0};
-    bool stop = false;
-};
 
 struct BlurSpec {
     float sigma = 0;

@@ -336,3 +336,19 @@ def test_order_replay_portable_dense_sort(tmp_path):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", *defs, "-o", exe, src])
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0 and "cases agree" in out.stdout, out.stdout
+
+
+def test_worker_pool_back_to_back_jobs(tmp_path):
+    """sift_b200/csrc/pool.h under sift_gpu_run's usage pattern (two pools, the next job begun right after the previous one
+    was joined): every item exactly once, no hang — also under ThreadSanitizer where the toolchain has it
+    (tests/native/pool_check.cpp).  The first version of the pool let a worker that was still leaving job k draw from job k+1."""
+    src = os.path.join(ROOT, "tests", "native", "pool_check.cpp")
+    exe = str(tmp_path / "pool_check")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, src, "-lpthread"])
+    out = subprocess.run([exe, "20000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "pool ok" in out.stdout, out.stdout + out.stderr
+    tsan = str(tmp_path / "pool_check_tsan")
+    if subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-o", tsan, src, "-lpthread"],
+                      capture_output=True).returncode == 0:
+        out = subprocess.run([tsan, "2000"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "pool ok" in out.stdout and "WARNING: ThreadSanitizer" not in out.stderr, out.stdout + out.stderr
