@@ -331,7 +331,7 @@ def run_ours(args):
     if args.quick_e2e:
         # development: only the end-to-end leg, with and without the packed upload (SIFT_GPU_HOST_PACK), one line
         out = {}
-        for mode in ("default", "0", "1"):
+        for mode in ("default", "0", "1", "2"):
             if mode == "default":
                 os.environ.pop("SIFT_GPU_HOST_PACK", None)
             else:

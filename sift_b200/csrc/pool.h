@@ -48,6 +48,23 @@ class Pool {
         done_cv.wait(lk, [this] { return pending.load() == 0; });
         active = false;
     }
+    // Between begin() and end(): no further items are started.  Returns how many were (items 0 .. result-1 run to completion, the
+    // caller's end() waits for the ones still in flight and then runs nothing itself).
+    int cancel_rest() {
+        const int n = held_n;
+        if (n <= 0) return 0;
+        if (workers.empty()) { held_n = 0; return 0; }
+        const uint64_t exhausted = ((uint64_t)gen << 32) | (uint32_t)n;
+        uint64_t cur = ticket.load();
+        for (;;) {
+            const int drawn = (int)(uint32_t)cur;
+            if (drawn >= n) return n;
+            if (!ticket.compare_exchange_weak(cur, exhausted)) continue;  // cur reloaded
+            const int rest = n - drawn;
+            if (pending.fetch_sub(rest) == rest) { std::lock_guard<std::mutex> lk(m); done_cv.notify_all(); }
+            return drawn;
+        }
+    }
     void parallel_for(int n, const std::function<void(int)>& fn) {
         begin(n, fn);
         end();

@@ -165,7 +165,9 @@ struct Slot {
     uint8_t* h_pack = nullptr;      // pinned, B x max_in_px, laid out like d_in_u8
     bool pack_job = false;          // a packing job for this slot is on the pack pool
     std::atomic<int> pack_bad{0};   // some pixel of the pass is not an exact 8-bit value: the pass travels as f32
-    bool packed = false;            // stage A uploads h_pack instead of the caller's frames
+    int pack_blocks = 1;            // work items per image of the job
+    bool packed = false;            // stage A uploads the first n_packed frames from h_pack as bytes, the rest as they are
+    int n_packed = 0;
     // keypoint stage buffers (grow on demand)
     size_t key_cap = 0;
     KeyIn* d_keys = nullptr; KeyIn* h_keys = nullptr;
@@ -812,19 +814,23 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
     S.launches = 0;
     CTX_CUDA(cudaEventRecord(S.ev[0], s));
     // upload (main.cpp:52-54 leaves band 0 as float 0..255; u8 input is widened on the device)
-    if (S.packed) {
-        // the pass's f32 frames were packed to bytes on the host (pack_begin): same layout as d_in_u8, one transfer when dense
+    const int n_packed = S.packed ? S.n_packed : 0;
+    if (n_packed) {
+        // the first n_packed f32 frames of the pass were packed to bytes on the host (pack_begin): they go up as bytes (same
+        // layout as d_in_u8, one transfer when dense) and are widened right here, so that the rest of stage A is that of any
+        // f32 pass; the frames the host threads did not get to follow as they are
         const size_t img_bytes = (size_t)p->in_pitch * (size_t)p->in_h;
         if (img_bytes == c->max_in_px) {
-            CTX_CUDA(cudaMemcpyAsync(S.d_in_u8, S.h_pack, img_bytes * (size_t)nb, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(cudaMemcpyAsync(S.d_in_u8, S.h_pack, img_bytes * (size_t)n_packed, cudaMemcpyHostToDevice, s));
         } else {
-            for (int b = 0; b < nb; ++b)
+            for (int b = 0; b < n_packed; ++b)
                 CTX_CUDA(cudaMemcpyAsync(S.d_in_u8 + (size_t)b * c->max_in_px, S.h_pack + (size_t)b * c->max_in_px, img_bytes, cudaMemcpyHostToDevice, s));
         }
-        c->tm.h2d_bytes += img_bytes * (size_t)nb;
-        c->tm.packed_images += (uint32_t)nb;
+        CTX_TRY(launch_u8_to_f32(S.d_in_u8, c->max_in_px, p->in_pitch, S.d_in, c->max_in_px, p->in_pitch, p->in_w, p->in_h, n_packed, s, L));
+        c->tm.h2d_bytes += img_bytes * (size_t)n_packed;
+        c->tm.packed_images += (uint32_t)n_packed;
     }
-    for (int b = 0; b < nb && !S.packed;) {
+    for (int b = n_packed; b < nb;) {
         const sift_gpu_image& im = *S.imgs[(size_t)b].img;
         const size_t esz = im.dtype == SIFT_GPU_DTYPE_U8 ? 1 : 4;
         const size_t pitch = im.row_stride_bytes ? (size_t)im.row_stride_bytes : (size_t)im.width * esz;
@@ -853,7 +859,7 @@ static int enqueue_stage_a(sift_gpu_ctx* c, Slot& S, int slot_index) {
     // pyramid streams, the stage-boundary events as external event-record nodes) and from then on one graph launch
     // replaces ~50 launch calls — less host time per pass and shorter gaps between the short kernels of the small octaves.
     static const bool graphs_on = [] { const char* e = getenv("SIFT_GPU_GRAPHS"); return !(e && atoi(e) == 0) && !getenv("SIFT_GPU_TRACE_PYR"); }();
-    const bool u8 = S.packed || S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8;
+    const bool u8 = S.imgs[0].img->dtype == SIFT_GPU_DTYPE_U8;  // (packed frames belong to f32 passes and are widened above)
     Slot::StageGraph* G = graphs_on ? &S.graphs[std::make_tuple((const void*)p, nb, u8 ? 1 : 0)] : nullptr;
     if (G && G->exec) {
         CTX_CUDA(cudaGraphLaunch(G->exec, s));
@@ -1311,12 +1317,16 @@ extern "C" int sift_gpu_debug_pack_rows_u8(const float* src, size_t src_stride_b
 
 constexpr int kPackMinImages = 8;   // below this a pass is latency work: packing would only delay its upload
 constexpr int kPackRows = 128;      // rows per work item
+constexpr int kPackDefaultMode = 2;
 
-// Policy: SIFT_GPU_HOST_PACK=0 / 1 (read per run) turns it off / on; by default it is on when this context has at least 8
-// host threads to itself (a frame costs about a millisecond of one core: with fewer threads the order replay needs them more).
-static bool pack_enabled(const sift_gpu_ctx* c) {
-    if (const char* e = getenv("SIFT_GPU_HOST_PACK")) return atoi(e) != 0;
-    return c->host_threads >= 8;
+// Policy (read per run): SIFT_GPU_HOST_PACK=0 off; 1 whole passes (stage A waits until every frame of its pass is packed);
+// 2 split (stage A never waits: the frames packed by the time the pass is due travel as bytes, the rest as f32 — the host
+// threads and the PCIe link share the upload in whatever proportion they manage).  Default: split when this context has at
+// least 8 host threads to itself (a frame costs about a millisecond of one core: with fewer threads the order replay needs
+// them more), else off.
+static int pack_mode(const sift_gpu_ctx* c) {
+    if (const char* e = getenv("SIFT_GPU_HOST_PACK")) { const int v = atoi(e); return v < 0 ? 0 : (v > 2 ? 2 : v); }
+    return c->host_threads >= 8 ? kPackDefaultMode : 0;
 }
 
 // Starts packing the frames of pass `pp` into the slot's pinned staging buffer on the pack pool and returns; pack_end joins.
@@ -1339,6 +1349,7 @@ static int pack_begin(sift_gpu_ctx* c, Slot& S, const PassPlan& pp) {
     const int blocks = (p->in_h + kPackRows - 1) / kPackRows;
     S.pack_bad.store(0);
     S.pack_job = true;
+    S.pack_blocks = blocks;
     Slot* Sp = &S;
     const PassPlan* ppp = &pp;
     const size_t img_stride = c->max_in_px;
@@ -1355,12 +1366,18 @@ static int pack_begin(sift_gpu_ctx* c, Slot& S, const PassPlan& pp) {
     return 0;
 }
 
-static void pack_end(sift_gpu_ctx* c, Slot& S) {
+// Joins the slot's packing job.  `split`: items not yet started are dropped, only whole frames count.
+static void pack_end(sift_gpu_ctx* c, Slot& S, int nb, bool split) {
     S.packed = false;
+    S.n_packed = 0;
     if (!S.pack_job) return;
+    int items = nb * S.pack_blocks;
+    if (split) items = c->pack_pool->cancel_rest();
     c->pack_pool->end();
     S.pack_job = false;
-    S.packed = S.pack_bad.load() == 0;
+    if (S.pack_bad.load() != 0) return;
+    S.n_packed = std::min(nb, items / S.pack_blocks);
+    S.packed = S.n_packed > 0;
 }
 
 int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, sift_gpu_result* results) {
@@ -1448,7 +1465,8 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
             }
         return 0;
     };
-    const bool packing = pack_enabled(c);
+    const int packing = pack_mode(c);
+    const bool pack_early = lag_b >= 1 && ns >= 3;
     // frames of pass k+1 are packed on the second pool while pass k's stage A is enqueued and an earlier pass is replayed;
     // stage_a(k+1) joins that job before it uploads
     auto pack_ahead = [&](int k) -> int {
@@ -1462,7 +1480,9 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
         S.busy = true;
         if (k == 0) CTX_CUDA(cudaEventRecord(c->ev_first, S.stream));
         const double t_p0 = now_ms();
-        pack_end(c, S);
+        pack_end(c, S, (int)S.imgs.size(), packing == 2);
+        // pipelined loop: the host threads go straight on to the next pass (its slot's previous pass was uploaded iterations ago)
+        if (pack_early) CTX_TRY(pack_ahead(k + 1));
         g_trace[6] += now_ms() - t_p0;
         const double t_a0 = now_ms();
         CTX_TRY(enqueue_stage_a(c, S, k % ns));
@@ -1480,7 +1500,6 @@ int sift_gpu_run(sift_gpu_ctx* c, const sift_gpu_image* images, int n_images, si
             if (k - ns >= 0 && k - ns < np) CTX_TRY(collect(k - ns));
             if (k < np) CTX_TRY(stage_a(k));
             if (rb) CTX_TRY(end_replay_and_enqueue_stage_b(c, c->slots[kb % ns], kb % ns));
-            CTX_TRY(pack_ahead(k + 1));
         }
     } else {
         for (int k = 0; k < np + lag_f; ++k) {

@@ -23,9 +23,17 @@ int main(int argc, char** argv) {
         std::fill(a.begin(), a.begin() + nb, 0);
         replay.begin(nb, [&](int i) { a[(size_t)i] += 1; sum += 1; });
         expect += nb;
+        // every third round the rest of the pack job is cancelled (the split upload): items below the returned count ran exactly
+        // once, the others not at all
+        int ran = pack_n;
+        if (k % 3 == 1) {
+            ran = pack.cancel_rest();
+            if (ran < 0 || ran > pack_n) { std::printf("cancel_rest returned %d of %d\n", ran, pack_n); return 1; }
+            expect -= 2L * (pack_n - ran);
+        }
         pack.end();
         for (int i = 0; i < pack_n; ++i)
-            if (b[(size_t)i] != 1) { std::printf("pack item %d of round %d ran %d times\n", i, k, b[(size_t)i]); return 1; }
+            if (b[(size_t)i] != (i < ran ? 1 : 0)) { std::printf("pack item %d of round %d ran %d times (%d started)\n", i, k, b[(size_t)i], ran); return 1; }
         replay.end();
         for (int i = 0; i < nb; ++i)
             if (a[(size_t)i] != 1) { std::printf("replay item %d of round %d ran %d times\n", i, k, a[(size_t)i]); return 1; }

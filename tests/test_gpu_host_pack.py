@@ -11,6 +11,8 @@ from sift_b200.synth import synth_frame
 
 pytestmark = pytest.mark.gpu
 K = capi.SQRT2_F32
+# SIFT_GPU_HOST_PACK: "0" off, "1" whole passes (stage A waits for the packers: deterministic counts), "2" split (it does not:
+# whatever is packed when the pass is due goes up as bytes, the rest as f32)
 
 
 def same(a, b):
@@ -87,3 +89,27 @@ def test_packing_ahead_across_many_passes_and_small_or_non_f32_passes_are_left_a
         same(c[:8], a[:8]); same(c[8:16], a[:8]); same(c[16:], a[:8])
         g.close()
     vs_oracle(a[2], frames[2], 3)
+
+
+def test_split_upload_mixes_bytes_and_floats_inside_a_pass(built, monkeypatch):
+    """Mode 2 never waits for the packers: a pass goes up as n packed frames followed by nb - n raw ones, n anywhere in
+    [0, nb].  Whatever n turns out to be, the results are those of the plain upload and the counters add up."""
+    frames = [synth_frame(192, 144, 60 + s) for s in range(6)]
+    seq = [frames[i % 6] for i in range(44)]          # passes of 10, 10, 10, 10, 4
+    g = capi.SiftGpu(3, 3, max_width=192, max_height=144, max_batch=10)
+    monkeypatch.setenv("SIFT_GPU_HOST_PACK", "0")
+    ref = g.run(seq)
+    monkeypatch.setenv("SIFT_GPU_HOST_PACK", "2")
+    seen = set()
+    for _ in range(4):
+        a, t = g.run(seq), g.timings()
+        n = int(t["packed_images"])
+        assert 0 <= n <= 40
+        assert t["h2d_bytes"] == n * 192 * 144 + (44 - n) * 192 * 144 * 4
+        same(a, ref)
+        seen.add(n)
+    monkeypatch.delenv("SIFT_GPU_HOST_PACK")          # the library's own policy
+    same(g.run(seq), ref)
+    vs_oracle(a[3], frames[3], 3)
+    vs_oracle(a[43], frames[43 % 6], 3)
+    g.close()
