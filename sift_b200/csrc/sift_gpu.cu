@@ -1317,13 +1317,13 @@ extern "C" int sift_gpu_debug_pack_rows_u8(const float* src, size_t src_stride_b
 
 constexpr int kPackMinImages = 8;   // below this a pass is latency work: packing would only delay its upload
 constexpr int kPackRows = 128;      // rows per work item
-constexpr int kPackDefaultMode = 2;
+constexpr int kPackDefaultMode = 1;  // measured on one B200 with 16 host threads: whole passes 12.3 k images/s, split 9.4 k, off 6.3 k
 
 // Policy (read per run): SIFT_GPU_HOST_PACK=0 off; 1 whole passes (stage A waits until every frame of its pass is packed);
 // 2 split (stage A never waits: the frames packed by the time the pass is due travel as bytes, the rest as f32 — the host
-// threads and the PCIe link share the upload in whatever proportion they manage).  Default: split when this context has at
-// least 8 host threads to itself (a frame costs about a millisecond of one core: with fewer threads the order replay needs
-// them more), else off.
+// threads and the PCIe link share the upload in whatever proportion they manage; measured slower than 1 where the host has
+// the threads, kept for hosts that do not).  Default: whole passes when this context has at least 8 host threads to itself
+// (a frame costs about a millisecond of one core: with fewer threads the order replay needs them more), else off.
 static int pack_mode(const sift_gpu_ctx* c) {
     if (const char* e = getenv("SIFT_GPU_HOST_PACK")) { const int v = atoi(e); return v < 0 ? 0 : (v > 2 ? 2 : v); }
     return c->host_threads >= 8 ? kPackDefaultMode : 0;
