@@ -352,7 +352,8 @@ def run_ours(args):
     # threads inside the call (lossless, include/sift_gpu.h) where its policy allows; the bytes that travelled are its own count.
     wall_h, acc_h, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
     wall_f32, acc_f32 = wall_h, acc_h
-    if acc_h["packed"]:
+    (any_packed,), _ = shard.reduce_max_sum(dist, dev, [float(acc_h["packed"] > 0)], [0.0])  # every rank takes the same branch (barriers inside)
+    if any_packed:
         # supplementary: the same call with the packing switched off (every frame travels as 4 bytes per pixel)
         os.environ["SIFT_GPU_HOST_PACK"] = "0"
         wall_f32, acc_f32, _ = timed(host_frames.data_ptr(), capi.MEM_HOST)
