@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol(built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sift_gpu.h but not exported"
     assert sorted(capi.EXPORTED_SYMBOLS) == names
-    assert b"sm_100a" in lib.sift_gpu_version.__call__() if False else True
+    lib.sift_gpu_version.restype = C.c_char_p
+    assert b"sm_100a" in lib.sift_gpu_version()
 
 
 def test_no_cpu_fallback_create_fails_without_gpu(built):
