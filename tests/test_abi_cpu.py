@@ -353,3 +353,14 @@ def test_worker_pool_back_to_back_jobs(tmp_path):
                       capture_output=True).returncode == 0:
         out = subprocess.run([tsan, "2000"], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and "pool ok" in out.stdout and "WARNING: ThreadSanitizer" not in out.stderr, out.stdout + out.stderr
+
+
+def test_frame_packer_stays_inside_its_rows(tmp_path):
+    """tests/native/pack_check.cpp: pack_host.cpp on ragged shapes with exact-size buffers, under ASan/UBSan where available."""
+    srcs = [os.path.join(ROOT, "tests", "native", "pack_check.cpp"), os.path.join(ROOT, "sift_b200", "csrc", "pack_host.cpp")]
+    exe = str(tmp_path / "pack_check")
+    san = ["-fsanitize=address,undefined"]
+    if subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++17", *san, "-o", exe, *srcs], capture_output=True).returncode != 0:
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, *srcs])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "pack edge cases ok" in out.stdout, out.stdout + out.stderr
