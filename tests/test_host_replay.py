@@ -111,3 +111,75 @@ def test_frame_packing_ragged_widths_strides_and_pitches(w):
     assert o is not None and np.array_equal(o, a.astype(np.uint8))
     big[6, w - 1] = 7.5
     assert capi.pack_u8(big[:, :w]) is None
+
+
+# ---- randomized: replay_image against a numpy model of sift.cpp:37-55 built on the real std::sort ------------------
+def _model(w, h, octaves, dpe, n_cand, canon, xs, ys, oc, ix, sigma=1.6, k=capi.SQRT2_F32):
+    """sift.cpp:37-55 spelled out: std::sort(cmpByFilter) over the whole candidate vector (the library's debug entry runs
+    the real std::sort), u16 size, orientation-stage bounds test, second sort + u16 size, descriptor-stage bounds test."""
+    flags = np.ones(n_cand, np.uint8)
+    flags[canon] = 0
+    order = capi.sort_order(flags)                                  # real std::sort permutation of the n_cand elements
+    pos_of = np.full(n_cand, -1, np.int64)
+    pos_of[canon] = np.arange(canon.size)
+    n1 = canon.size % 65536                                         # (uint16_t) count
+    l1 = pos_of[order[:n1]]                                         # survivor slots in vector order
+    assert (l1 >= 0).all()
+    # nearest Gaussian level of every DoG class, as Sift::_findNearestGaussian (sift.cpp:205-218) over the schedule of :381-417
+    g = np.zeros((octaves, dpe + 1), np.float32)
+    g[0, 0] = sigma
+    e = 0
+    for o in range(octaves):
+        for j in range(1, dpe + 1):
+            g[o, j] = np.float32(np.float64(k) ** e * np.float64(np.float32(sigma)))
+            e += 1
+        if o < octaves - 1:
+            g[o + 1, 0] = g[o, dpe - 1]
+            e -= 2
+    d = g[:, 1:] - g[:, :-1]
+    dims = [(w, h)]
+    for _ in range(1, octaves):
+        dims.append(((dims[-1][0] + 1) // 2, (dims[-1][1] + 1) // 2))
+
+    def target_dims(o, i):
+        best, bo = np.float32(100), 0
+        for oo in range(octaves):
+            for ii in range(dpe + 1):
+                cur = np.abs(np.float32(g[oo, ii] - d[o, i]))
+                if cur < best:
+                    best, bo = cur, oo
+        return dims[bo]
+
+    tw = np.array([target_dims(o, i)[0] for o, i in zip(oc[l1], ix[l1])], np.int64)
+    th = np.array([target_dims(o, i)[1] for o, i in zip(oc[l1], ix[l1])], np.int64)
+    x, y = xs[l1].astype(np.int64), ys[l1].astype(np.int64)
+    outside = (x < 8) | (x >= tw - 8) | (y < 8) | (y >= th - 8)      # sift.cpp:173-178
+    order2 = capi.sort_order(outside.astype(np.uint8))
+    n2 = int((~outside).sum()) % 65536
+    kept = order2[:n2]
+    rej = (x[kept] < 8) | (x[kept] > tw[kept] - 8) | (y[kept] < 8) | (y[kept] > th[kept] - 8)   # sift.cpp:65-70
+    return n1, l1[kept], rej, d
+
+
+@pytest.mark.parametrize("seed,w,h,octaves,dpe,n_cand,density", [
+    (0, 320, 240, 3, 3, 5000, 0.02), (1, 320, 240, 3, 3, 5000, 0.5), (2, 211, 157, 2, 4, 20000, 0.1),
+    (3, 1920, 1080, 5, 3, 140000, 0.014), (4, 1120, 1120, 1, 3, 200000, 0.45), (5, 64, 64, 2, 3, 40, 0.3),
+    (6, 640, 480, 4, 3, 70000, 0.97), (7, 97, 131, 3, 3, 17, 1.0), (8, 400, 300, 3, 3, 3000, 0.0)])
+def test_host_replay_random_lists_against_the_std_sort_model(seed, w, h, octaves, dpe, n_cand, density):
+    rng = np.random.default_rng(seed)
+    canon = np.flatnonzero(rng.uniform(size=n_cand) < density).astype(np.uint32)
+    m = canon.size
+    oc = rng.integers(0, octaves, m).astype(np.uint8)
+    ix = rng.integers(1, dpe - 1, m).astype(np.uint8) if dpe > 3 else np.ones(m, np.uint8)
+    ow = np.array([max(1, (w + (1 << o) - 1) >> o) for o in range(octaves)])
+    oh = np.array([max(1, (h + (1 << o) - 1) >> o) for o in range(octaves)])
+    xs = (rng.uniform(size=m) * ow[oc]).astype(np.uint16)           # anywhere in the point's octave: the bounds tests must bite
+    ys = (rng.uniform(size=m) * oh[oc]).astype(np.uint16)
+    got, n_surv = capi.host_replay(w, h, n_cand, canon, xs, ys, oc, ix, dogs_per_epoch=dpe, octaves=octaves)
+    n1, slots, rej, d = _model(w, h, octaves, dpe, n_cand, canon, xs, ys, oc, ix)
+    assert n_surv == n1 and got.size == slots.size
+    assert np.array_equal(got["x"], xs[slots]) and np.array_equal(got["y"], ys[slots])
+    assert np.array_equal(got["octave"], oc[slots]) and np.array_equal(got["index"], ix[slots])
+    assert np.array_equal(got["filtered"], rej.astype(np.uint8))
+    assert np.array_equal(got["desc_len"], np.where(rej, 0, 128).astype(np.uint8))
+    assert np.array_equal(got["scale"], d[oc[slots], ix[slots]])
