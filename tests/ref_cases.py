@@ -98,3 +98,28 @@ def stage_digests(o, kp, p):
     d["kp_desc"] = digest(kp["desc"])
     d["text"] = hashlib.sha256(o.text().encode()).hexdigest()[:32]
     return d
+
+
+def pyramid_and_point_digests(o, kp, p):
+    """The stages the shipped executable can be made to show (tests/refbin.py): every Gaussian and DoG level with its scale
+    label, the candidate list with the elimination flags, the final keypoints with orientation and descriptors.  Same keys
+    and digests as stage_digests(), minus the intermediate survivor list and the result text."""
+    d = {"n_keypoints": int(kp["x"].size)}
+    for oc in range(p["octaves"]):
+        for i in range(p["dpe"] + 1):
+            g, s = o.gauss(oc, i)
+            d[f"gauss_{oc}_{i}"] = digest(g)
+            d[f"gauss_scale_{oc}_{i}"] = float(s)
+        for i in range(p["dpe"]):
+            g, s = o.dog(oc, i)
+            d[f"dog_{oc}_{i}"] = digest(g)
+            d[f"dog_scale_{oc}_{i}"] = float(s)
+    c = o.candidates()
+    d["n_candidates"] = int(c["x"].size)
+    d["n_unfiltered"] = int((c["filtered"] == 0).sum())
+    for f in ("x", "y", "octave", "index", "filtered", "scale"):
+        d[f"cand_{f}"] = digest(c[f])
+    for f in ("x", "y", "octave", "index", "scale", "orientation", "filtered", "desc_len"):
+        d[f"kp_{f}"] = digest(kp[f])
+    d["kp_desc"] = digest(kp["desc"])
+    return d

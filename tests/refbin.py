@@ -1,0 +1,115 @@
+"""Drives oracle/_ref/refbin_run (oracle/refbin_run.cpp): code of the reference's SHIPPED EXECUTABLE
+(/root/reference/bin/arch_x64/sift — GCC 7, real Vigra 1.11 compiled in) called in place.  TEST INFRASTRUCTURE ONLY.
+
+`run_stages(img, dpe, octaves, sigma, k, subpixel)` returns an object with the accessors of oracle_lib.Oracle
+(gauss, dog, candidates, keypoints) filled from what the executable's own Sift::_createDOGs, _findScaleSpaceExtrema,
+_eliminateEdgeResponses and Sift::calculate produced, or None when the executable left with a vigra exception."""
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.environ.get("SIFT_REF_EXE", "/root/reference/bin/arch_x64/sift")
+RUN = os.path.join(ROOT, "oracle", "_ref", "refbin_run")
+
+
+def available():
+    return os.path.exists(EXE) and os.path.exists(RUN)
+
+
+class Stages:
+    def __init__(self, octaves, dpe, g, d, cands, kps):
+        self.octaves, self.dpe, self._g, self._d, self._c, self._k = octaves, dpe, g, d, cands, kps
+
+    def gauss(self, o, i):
+        return self._g[o, i]
+
+    def dog(self, o, i):
+        return self._d[o, i]
+
+    def candidates(self):
+        return self._c
+
+    def keypoints(self):
+        return self._k
+
+
+def _points(buf, off, with_desc):
+    (n,) = struct.unpack_from("<i", buf, off)
+    off += 4
+    d = dict(x=np.zeros(n, np.uint16), y=np.zeros(n, np.uint16), octave=np.zeros(n, np.uint16), index=np.zeros(n, np.uint16),
+             scale=np.zeros(n, np.float32), filtered=np.zeros(n, np.uint8))
+    if with_desc:
+        d["orientation"] = np.zeros(n, np.float32)
+        d["desc"] = np.zeros((n, 128), np.float32)
+        d["desc_len"] = np.zeros(n, np.int32)
+    for j in range(n):
+        x, y, oc, ix, sc, ori, fl = struct.unpack_from("<HHHHffB", buf, off)
+        off += 17
+        d["x"][j], d["y"][j], d["octave"][j], d["index"][j], d["scale"][j], d["filtered"][j] = x, y, oc, ix, sc, fl
+        if with_desc:
+            (nd,) = struct.unpack_from("<i", buf, off)
+            off += 4
+            d["orientation"][j], d["desc_len"][j] = ori, nd
+            d["desc"][j, :nd] = np.frombuffer(buf, np.float32, nd, off)
+            off += 4 * nd
+    return d, off
+
+
+def _call(cmd, payload, timeout):
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(payload)
+        r = subprocess.run([RUN, EXE, cmd, fin, fout], capture_output=True, text=True, timeout=timeout)
+        if r.returncode not in (0, 3):
+            raise RuntimeError(f"refbin_run failed ({r.returncode}): {r.stderr[-400:]}")
+        with open(fout, "rb") as f:
+            return r.returncode, f.read()
+
+
+def run_stages(img, dpe, octaves, sigma, k, subpixel, timeout=1200):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    rc, buf = _call("stages", struct.pack("<iiiiffi", w, h, dpe, octaves, sigma, k, int(subpixel)) + img.tobytes(), timeout)
+    if rc == 3:
+        return None   # vigra::PreconditionViolation (or another std::exception) left the executable's code
+    off = 0
+    O, D = struct.unpack_from("<ii", buf, off)
+    off += 8
+
+    def image():
+        nonlocal off
+        ww, hh, sc = struct.unpack_from("<iif", buf, off)
+        off += 12
+        a = np.frombuffer(buf, np.float32, ww * hh, off).reshape(hh, ww).copy()
+        off += 4 * ww * hh
+        return a, sc
+
+    g, d = {}, {}
+    for o in range(O):
+        for i in range(D + 1):
+            g[o, i] = image()
+        for i in range(D):
+            d[o, i] = image()
+    cands, off = _points(buf, off, False)
+    kps, off = _points(buf, off, True)
+    assert off == len(buf)
+    return Stages(O, D, g, d, cands, kps)
+
+
+def run_unit(img, sigma, timeout=300):
+    """alg::convolveWithGauss, reduceToNextLevel, increaseToNextLevel of the executable on one image."""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    _, buf = _call("unit", struct.pack("<iif", w, h, sigma) + img.tobytes(), timeout)
+    out, off = [], 0
+    for _ in range(3):
+        ww, hh, _sc = struct.unpack_from("<iif", buf, off)
+        off += 12
+        out.append(np.frombuffer(buf, np.float32, ww * hh, off).reshape(hh, ww).copy())
+        off += 4 * ww * hh
+    return out
