@@ -16,6 +16,10 @@
 //        _eliminateEdgeResponses (flags included), and the result vector of Sift::calculate on a fresh object
 //        (see dump_* below for the record formats)
 //        refbin_run <executable> unit <in> <out>      alg::convolveWithGauss / reduceToNextLevel / increaseToNextLevel on one image
+//        refbin_run <executable> eliminate <in> <out> Sift::_eliminateEdgeResponses (Vigra's inverse + linearSolve inside) on three
+//                                                     caller-supplied DoG layers and a list of points; out: one flag per point
+//        refbin_run <executable> vertex <in> <out>    alg::vertexParabola on n point triples (the rank-deficient least squares)
+//        refbin_run <executable> peaks <in> <out>     Sift::_findPeaks on n 36-bin histograms; out per histogram: i32 count, the set
 //
 // Never part of the product; tests/test_refbin_pin.py is its only user and runs where /root/reference exists.
 #include <dlfcn.h>
@@ -30,7 +34,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <array>
 #include <new>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -311,6 +317,57 @@ int main(int argc, char** argv) {
             for (const char* n : names) {
                 VArr* r = new VArr(exe.fn<ImgFn>(n)(*img, hd.sigma));
                 dump_image(out, *r, hd.sigma);
+            }
+        } else if (cmd == "eliminate") {
+            // in: i32 w, h, n; three w*h f32 layers (row-major); n x (u16 x, u16 y)
+            struct Hdr { int32_t w, h, n; };
+            Hdr hd;
+            if (in.size() < sizeof(Hdr)) die("short input");
+            std::memcpy(&hd, in.data(), sizeof hd);
+            const size_t px = (size_t)hd.w * (size_t)hd.h;
+            if (in.size() != sizeof(Hdr) + 3 * sizeof(float) * px + 4 * (size_t)hd.n) die("input size does not match its header");
+            const float* layers = reinterpret_cast<const float*>(in.data() + sizeof(Hdr));
+            const uint16_t* xy = reinterpret_cast<const uint16_t*>(in.data() + sizeof(Hdr) + 3 * sizeof(float) * px);
+            // sift::Matrix<OctaveElem>(1, 3): one octave, three DoGs, element (0, i) at index i
+            ROctaveElem* elems = static_cast<ROctaveElem*>(::operator new(sizeof(ROctaveElem) * 3));
+            for (int i = 0; i < 3; ++i) {
+                elems[i].scale = 1.0f + (float)i;
+                new (&elems[i].img) VArr(layers + (size_t)i * px, hd.w, hd.h);
+            }
+            RMatrix* dogs = new RMatrix();
+            dogs->width = 1; dogs->height = 3;
+            dogs->data = std::shared_ptr<ROctaveElem>(elems, [](ROctaveElem*) {});
+            Points* pts = new Points();
+            for (int j = 0; j < hd.n; ++j) pts->push_back(sift::InterestPoint(sift::Point<u16_t, u16_t>(xy[2 * j], xy[2 * j + 1]), 2.0f, 0, 1));
+            RSift* s = make_sift(3, 1, 1.6f, 1.4142135f, false);
+            exe.fn<ElimFn>("_ZNK4sift4Sift23_eliminateEdgeResponsesERSt6vectorINS_13InterestPointESaIS2_EERKNS_6MatrixINS_10OctaveElemEEE")(s, *pts, *dogs);
+            for (const sift::InterestPoint& p : *pts) put<uint8_t>(out, p.filtered ? 1 : 0);
+        } else if (cmd == "vertex") {
+            // in: i32 n; n x (u16 lx, f32 ly, u16 px, f32 py, u16 rx, f32 ry) packed as 6 f32 (x values as floats holding integers)
+            typedef float (*VertexFn)(const sift::Point<u16_t, f32_t>&, const sift::Point<u16_t, f32_t>&, const sift::Point<u16_t, f32_t>&);
+            int32_t n;
+            std::memcpy(&n, in.data(), 4);
+            if (in.size() != 4 + (size_t)n * 24) die("input size does not match its header");
+            const float* v = reinterpret_cast<const float*>(in.data() + 4);
+            VertexFn f = exe.fn<VertexFn>("_ZN4sift3alg14vertexParabolaERKNS_5PointItfEES4_S4_");
+            for (int j = 0; j < n; ++j) {
+                const sift::Point<u16_t, f32_t> a((u16_t)v[6 * j], v[6 * j + 1]), b((u16_t)v[6 * j + 2], v[6 * j + 3]), c((u16_t)v[6 * j + 4], v[6 * j + 5]);
+                put<float>(out, f(a, b, c));
+            }
+        } else if (cmd == "peaks") {
+            // in: i32 n; n x 36 f32
+            typedef std::set<float> (*PeaksFn)(const RSift*, const std::array<float, 36>&);
+            int32_t n;
+            std::memcpy(&n, in.data(), 4);
+            if (in.size() != 4 + (size_t)n * 144) die("input size does not match its header");
+            PeaksFn f = exe.fn<PeaksFn>("_ZNK4sift4Sift10_findPeaksERKSt5arrayIfLm36EE");
+            RSift* s = make_sift(3, 3, 1.6f, 1.4142135f, false);
+            for (int j = 0; j < n; ++j) {
+                std::array<float, 36> h;
+                std::memcpy(h.data(), in.data() + 4 + (size_t)j * 144, 144);
+                std::set<float>* r = new std::set<float>(f(s, h));
+                put<int32_t>(out, (int32_t)r->size());
+                for (float x : *r) put<float>(out, x);
             }
         } else {
             die("unknown command", cmd.c_str());

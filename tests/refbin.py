@@ -113,3 +113,32 @@ def run_unit(img, sigma, timeout=300):
         out.append(np.frombuffer(buf, np.float32, ww * hh, off).reshape(hh, ww).copy())
         off += 4 * ww * hh
     return out
+
+
+def run_eliminate(d0, d1, d2, xs, ys, timeout=600):
+    """Sift::_eliminateEdgeResponses of the executable (Vigra's own inverse + linearSolve) on three DoG layers: one flag per point."""
+    d = [np.ascontiguousarray(a, np.float32) for a in (d0, d1, d2)]
+    h, w = d[1].shape
+    xy = np.stack([np.asarray(xs, np.uint16), np.asarray(ys, np.uint16)], axis=1).astype(np.uint16)
+    _, buf = _call("eliminate", struct.pack("<iii", w, h, xy.shape[0]) + b"".join(a.tobytes() for a in d) + xy.tobytes(), timeout)
+    return np.frombuffer(buf, np.uint8).copy()
+
+
+def run_vertex(triples, timeout=120):
+    """alg::vertexParabola of the executable on rows (lx, ly, px, py, rx, ry)."""
+    t = np.ascontiguousarray(triples, np.float32).reshape(-1, 6)
+    _, buf = _call("vertex", struct.pack("<i", t.shape[0]) + t.tobytes(), timeout)
+    return np.frombuffer(buf, np.float32).copy()
+
+
+def run_peaks(histos, timeout=120):
+    """Sift::_findPeaks of the executable on rows of 36 bins: list of the returned std::set contents (ascending, NaN as stored)."""
+    hs = np.ascontiguousarray(histos, np.float32).reshape(-1, 36)
+    _, buf = _call("peaks", struct.pack("<i", hs.shape[0]) + hs.tobytes(), timeout)
+    out, off = [], 0
+    for _ in range(hs.shape[0]):
+        (n,) = struct.unpack_from("<i", buf, off)
+        off += 4
+        out.append(np.frombuffer(buf, np.float32, n, off).copy())
+        off += 4 * n
+    return out

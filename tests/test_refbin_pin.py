@@ -106,3 +106,58 @@ def test_executables_blur_reduce_increase(w, h, sigma, seed):
     assert np.array_equal(blur, ol.convolve(img, sigma))
     assert np.array_equal(red, ol.reduce(img, sigma))
     assert np.array_equal(inc, ol.increase(img, sigma))
+
+
+@live
+@pytest.mark.parametrize("seed", range(6))
+def test_executables_elimination_with_vigras_own_linear_algebra(seed):
+    """Sift::_eliminateEdgeResponses of the executable — vigra::linalg::inverse and linearSolve (Householder QR with Vigra's
+    rank rule) as Vigra compiled them — on EVERY interior pixel of random DoG stacks: smooth ones, quantised ones full of ties
+    and singular Hessians, steep ones.  One flag per pixel, equal to the oracle's (and so to the CUDA kernel's, which the GPU
+    tests hold to the oracle on the same construction)."""
+    rng = np.random.default_rng(seed)
+    w, h = 61 + seed, 47
+    if seed == 3:    # quantised values: ties, zero Hessians (inverse() fails), rank-deficient systems
+        d = [rng.integers(126, 131, (h, w)).astype(np.float32) for _ in range(3)]
+    elif seed == 4:  # pure noise around 128: every branch of the reject chain
+        d = [(128 + rng.normal(0, 6, (h, w))).astype(np.float32) for _ in range(3)]
+    elif seed == 5:  # two identical layers: the scale derivatives vanish
+        a = (128 + rng.normal(0, 3, (h, w))).astype(np.float32)
+        d = [a, a.copy(), (128 + rng.normal(0, 3, (h, w))).astype(np.float32)]
+    else:
+        base = ol.convolve(rng.uniform(0, 255, (h, w)).astype(np.float32), 1.6)
+        d = [np.float32(128) + (ol.convolve(base, s) - base) * np.float32(g) for s, g in ((1.6, 1), (2.26, 3), (3.2, 5))]
+    gx, gy = np.meshgrid(np.arange(1, w - 1), np.arange(1, h - 1), indexing="ij")
+    gx, gy = gx.ravel().astype(np.uint16), gy.ravel().astype(np.uint16)
+    fb, fo = refbin.run_eliminate(*d, gx, gy), ol.eliminate(*d, gx, gy)
+    assert fb.size == fo.size == gx.size
+    assert np.array_equal(fb, fo), f"{int((fb != fo).sum())} of {fb.size} flags differ"
+    assert 0 < int(fb.sum())
+
+
+@live
+def test_executables_vertex_parabola_and_peaks():
+    rng = np.random.default_rng(8)
+    rows = [(355, 0.0, 5, 1234.5, 15, 0.0), (355, 0.0, 5, 10.0, 15, 0.0), (5, 0.0, 15, 0.0, 25, 0.0)]
+    for _ in range(300):
+        lx, px, rx = (int(v) for v in rng.choice(np.arange(5, 360, 10), 3, replace=False))
+        ly, py, ry = (float(np.float32(v)) for v in rng.uniform(0, 5000, 3))
+        rows.append((lx, ly, px, py, rx, ry))
+    got = refbin.run_vertex(rows)
+    want = np.array([ol.vertex_parabola(int(r[0]), r[1], int(r[2]), r[3], int(r[4]), r[5]) for r in rows], np.float32)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert abs(got[1] - 177.4913) < 1e-3        # SURVEY F3: what every orientation comes out as
+    hs = []
+    for trial in range(300):
+        hh = rng.uniform(0, 100, 36).astype(np.float32)
+        if trial % 4 == 0:
+            hh[rng.integers(0, 36, 30)] = 0
+        if trial % 7 == 0:
+            hh[:] = 0                           # all-zero histogram: 0/0 vertex, NaN in a std::set
+            hh[rng.integers(0, 36)] = trial
+        if trial % 5 == 0:
+            hh[rng.integers(0, 36, 3)] = hh.max()   # equal maxima
+        hs.append(hh)
+    for trial, (a, hh) in enumerate(zip(refbin.run_peaks(hs), hs)):
+        b = ol.find_peaks(hh)
+        assert a.size == b.size and np.array_equal(a, b, equal_nan=True), trial
