@@ -7,8 +7,9 @@
 //
 // What this pins: the reference's 640 lines of control flow, float/double promotions, iteration orders, the
 // real std::sort over real sift::InterestPoint objects, the u16 truncation — by the compiler, not by
-// transcription.  What stays restated: the Vigra routines behind the shim (Gaussian taps, reflect line
-// convolution, nearest-neighbour resize walk, Householder QR inverse / linearSolve) and the result-text
+// transcription.  What stays restated HERE: the Vigra routines behind the shim (Gaussian taps, reflect line
+// convolution, nearest-neighbour resize walk, Householder QR inverse / linearSolve) — those are pinned by the
+// reference's shipped executable instead (refbin_run.cpp, tests/test_refbin_pin.py) — and the result-text
 // writer (main.cpp:78-89; main.cpp needs Boost/OpenCV/Vigra-impex and is not compiled).
 #include <algorithm>
 #include <array>

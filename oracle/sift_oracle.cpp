@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see sift_oracle.hpp).
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Parity pinned against the reference's source build and its shipped executable (see sift_oracle.hpp).
 // CPU restatement of the reference's hot path; every function cites the reference lines it
 // follows (paths relative to the reference tree) and, where the arithmetic lives in Vigra,
 // the SURVEY.md Appendix A item (each confirmed in the reference's shipped binary).

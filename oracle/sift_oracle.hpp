@@ -1,10 +1,12 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see vigra_linalg.hpp header).  PARITY UNPINNED: the
-// reference has no tests/golden vectors and cannot be compiled here, so this
-// CPU restatement of snowiow/SIFT's hot path (loaded image -> keypoints + descriptors) is
-// anchored on the reference's own call sites (cited per function as file:line, relative to
-// the reference tree) plus the Vigra behaviour confirmed in its shipped binary (SURVEY.md
-// Appendix A).  Single-threaded, fp32 with the reference's few double detours, built -O3
-// without -march so that no FMA contraction can occur (the binary uses mulss/addss).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see vigra_linalg.hpp header).  PARITY PINNED: this CPU restatement of
+// snowiow/SIFT's hot path (loaded image -> keypoints + descriptors) is bit-identical, stage by stage, to (1) the reference's
+// own sift.cpp + algorithms.cpp compiled unmodified over Vigra stand-in headers (oracle/_ref, tests/test_ref_pin.py) and
+// (2) the reference's SHIPPED EXECUTABLE bin/arch_x64/sift — the author's GCC 7 build with the real Vigra 1.11 compiled in —
+// whose own functions are called in place (oracle/refbin_run.cpp, tests/test_refbin_pin.py), on every case that literal
+// build finishes in minutes; digests of both are committed under tests/golden/.  The reference itself holds no tests or
+// golden vectors.  Every function cites the reference lines it follows (file:line, relative to the reference
+// tree) and, where the arithmetic lives in Vigra, the SURVEY.md Appendix A item.  Single-threaded, fp32 with the reference's
+// few double detours, built -O3 without -march so that no FMA contraction can occur (the shipped binary uses mulss/addss).
 #pragma once
 #include <cstdint>
 #include <stdexcept>

@@ -1,8 +1,11 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is product code; only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 //
-// PARITY UNPINNED: the reference (snowiow/SIFT) ships no tests or golden vectors and cannot be
-// built here (Vigra, OpenCV-C++, Boost are absent).  This file restates the fp32 linear
+// PINNED BY EXECUTION: the reference (snowiow/SIFT) ships no tests or golden vectors and cannot be built here (Vigra,
+// OpenCV-C++, Boost are absent), but its shipped executable carries Vigra's own inverse / linearSolve: oracle/refbin_run.cpp
+// calls Sift::_eliminateEdgeResponses and alg::vertexParabola of that executable in place, and tests/test_refbin_pin.py holds
+// this file to them on every interior pixel of random DoG stacks (ties, singular Hessians included) and on whole images.
+// This file restates the fp32 linear
 // algebra of Vigra 1.11 (un-vendored dependency of the reference; SONAME libvigraimpex.so.11)
 // that the reference calls from
 //   sift.cpp:306        linalg::inverse(neg_sec_deriv, inverse_matrix)

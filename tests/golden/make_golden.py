@@ -1,7 +1,8 @@
 """Regenerates the small golden vectors under tests/golden/ from the CPU oracle (oracle/).
 
-The reference ships no golden vectors (parity unpinned), so these pin the ORACLE's
-outputs: they make its behaviour auditable and let the GPU tests run against committed numbers.
+The reference ships no golden vectors, so these record the ORACLE's outputs: they make its behaviour
+auditable and let the GPU tests run against committed numbers.  (The oracle itself is held to the reference's source build
+and to its shipped executable by tests/test_ref_pin.py and tests/test_refbin_pin.py.)
 Inputs are the seeded synthetic generator and a crop of the reference's example/parrot.jpg (band 0).
 """
 import os

@@ -7,8 +7,9 @@ stand-in headers (oracle/ref_shim/, oracle/Makefile target `ref`).  Three layers
   2. the restatement equals the live reference library stage by stage (runs wherever oracle/_ref was built);
   3. the reference's own alg:: functions and private stages, called one at a time on random inputs, equal the
      oracle's unit functions — and the copy-on-write build equals the deep-copy build.
-What stays restated on both sides (and therefore unpinned): the Vigra routines behind the shim — Gaussian taps,
-reflect line convolution, nearest-neighbour resize walk, Householder-QR inverse/linearSolve — see DESIGN.md §5."""
+What stays restated on both sides here: the Vigra routines behind the shim — Gaussian taps, reflect line convolution,
+nearest-neighbour resize walk, Householder-QR inverse/linearSolve; test_refbin_pin.py pins those against the reference's shipped
+executable (real Vigra 1.11 compiled in) — see DESIGN.md §5."""
 import json
 import os
 
