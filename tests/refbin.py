@@ -142,3 +142,11 @@ def run_peaks(histos, timeout=120):
         out.append(np.frombuffer(buf, np.float32, n, off).copy())
         off += 4 * n
     return out
+
+
+def time_calculate(img, dpe, octaves, sigma, k, subpixel, timeout=4 * 3600):
+    """Seconds the executable's own Sift::calculate takes on this host (one thread), and the number of keypoints."""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    _, buf = _call("time", struct.pack("<iiiiffi", w, h, dpe, octaves, sigma, k, int(subpixel)) + img.tobytes(), timeout)
+    return struct.unpack("<di", buf)
