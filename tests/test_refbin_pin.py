@@ -161,3 +161,25 @@ def test_executables_vertex_parabola_and_peaks():
     for trial, (a, hh) in enumerate(zip(refbin.run_peaks(hs), hs)):
         b = ol.find_peaks(hh)
         assert a.size == b.size and np.array_equal(a, b, equal_nan=True), trial
+
+
+@live
+@pytest.mark.parametrize("name", ["ragged", "sub_small", "sigma_k"])
+def test_product_host_replay_reproduces_the_executables_vector_order(name):
+    """The PRODUCT's host half (sift_gpu_debug_host_replay: both cleanup sorts replayed by order_replay.h, the u16 size, the
+    bounds tests) fed with the executable's own candidate list comes out in the executable's own keypoint order — the order
+    libstdc++ 7's std::sort, compiled into that binary, left the reference's vector in."""
+    from sift_b200 import capi
+
+    make, p, _, _ = rc.CASES[name]
+    img = make()
+    s = refbin.run_stages(img, p["dpe"], p["octaves"], p["sigma"], p["k"], p["subpixel"])
+    c, k = s.candidates(), s.keypoints()
+    keep = np.flatnonzero(c["filtered"] == 0).astype(np.uint32)
+    h, w = img.shape
+    got, _ = capi.host_replay(w, h, c["x"].size, keep, c["x"][keep], c["y"][keep], c["octave"][keep].astype(np.uint8),
+                              c["index"][keep].astype(np.uint8), dogs_per_epoch=p["dpe"], octaves=p["octaves"], sigma=p["sigma"],
+                              k=p["k"], subpixel=p["subpixel"])
+    assert got.size == k["x"].size > 0
+    for f in ("x", "y", "octave", "index", "scale", "filtered"):
+        assert np.array_equal(got[f], k[f]), f
