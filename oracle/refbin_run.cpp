@@ -15,6 +15,8 @@
 //   out: the Gaussian and DoG pyramids of Sift::_createDOGs, the candidate list after _findScaleSpaceExtrema +
 //        _eliminateEdgeResponses (flags included), and the result vector of Sift::calculate on a fresh object
 //        (see dump_* below for the record formats)
+//        refbin_run <executable> calculate <in> <out> same input; only Sift::calculate, out: the result vector (for frames on which
+//                                                     the stage-by-stage run, which does the work twice, would take too long)
 //        refbin_run <executable> time <in> <out>      same input as `stages`; only Sift::calculate, out: f64 seconds, i32 keypoints
 //        refbin_run <executable> unit <in> <out>      alg::convolveWithGauss / reduceToNextLevel / increaseToNextLevel on one image
 //        refbin_run <executable> eliminate <in> <out> Sift::_eliminateEdgeResponses (Vigra's inverse + linearSolve inside) on three
@@ -304,6 +306,16 @@ int main(int argc, char** argv) {
             RSift* s2 = make_sift(hd.dpe, hd.octaves, hd.sigma, hd.k, hd.subpixel != 0);
             VArr* img2 = new VArr(px, hd.w, hd.h);
             Points* res = new Points(exe.fn<CalcFn>("_ZN4sift4Sift9calculateERN5vigra10MultiArrayILj2EfSaIfEEE")(s2, *img2));
+            dump_points(out, *res, true);
+        } else if (cmd == "calculate") {
+            struct Hdr { int32_t w, h, dpe, octaves; float sigma, k; int32_t subpixel; };
+            Hdr hd;
+            if (in.size() < sizeof(Hdr)) die("short input");
+            std::memcpy(&hd, in.data(), sizeof hd);
+            if (in.size() != sizeof(Hdr) + sizeof(float) * (size_t)hd.w * (size_t)hd.h) die("input size does not match its header");
+            RSift* s = make_sift(hd.dpe, hd.octaves, hd.sigma, hd.k, hd.subpixel != 0);
+            VArr* img = new VArr(reinterpret_cast<const float*>(in.data() + sizeof(Hdr)), hd.w, hd.h);
+            Points* res = new Points(exe.fn<CalcFn>("_ZN4sift4Sift9calculateERN5vigra10MultiArrayILj2EfSaIfEEE")(s, *img));
             dump_points(out, *res, true);
         } else if (cmd == "time") {
             struct Hdr { int32_t w, h, dpe, octaves; float sigma, k; int32_t subpixel; };

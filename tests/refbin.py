@@ -150,3 +150,24 @@ def time_calculate(img, dpe, octaves, sigma, k, subpixel, timeout=4 * 3600):
     h, w = img.shape
     _, buf = _call("time", struct.pack("<iiiiffi", w, h, dpe, octaves, sigma, k, int(subpixel)) + img.tobytes(), timeout)
     return struct.unpack("<di", buf)
+
+
+def run_calculate(img, dpe, octaves, sigma, k, subpixel, timeout=8 * 3600):
+    """Only the executable's Sift::calculate: the keypoint dict (orientation and descriptors included), or None on a vigra exception."""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    rc, buf = _call("calculate", struct.pack("<iiiiffi", w, h, dpe, octaves, sigma, k, int(subpixel)) + img.tobytes(), timeout)
+    if rc == 3:
+        return None
+    kps, off = _points(buf, 0, True)
+    assert off == len(buf)
+    return kps
+
+
+def unit_exception(img, sigma, timeout=120):
+    """None when the executable's convolveWithGauss, reduceToNextLevel and increaseToNextLevel all return on `img`, else the
+    what() of the vigra exception the first failing one left with."""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    rc, buf = _call("unit", struct.pack("<iif", w, h, sigma) + img.tobytes(), timeout)
+    return buf[4:].decode(errors="replace") if rc == 3 else None

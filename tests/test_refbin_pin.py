@@ -183,3 +183,26 @@ def test_product_host_replay_reproduces_the_executables_vector_order(name):
     assert got.size == k["x"].size > 0
     for f in ("x", "y", "octave", "index", "scale", "filtered"):
         assert np.array_equal(got[f], k[f]), f
+
+
+@live
+@pytest.mark.parametrize("w,h,sigma", [(5, 20, 1.6), (6, 20, 1.6), (20, 5, 1.6), (20, 6, 1.6), (10, 10, 3.2), (11, 11, 3.2), (2, 2, 0.3),
+                                       (1, 1, 0.3), (2, 1, 0.3), (3, 3, 0.5), (4, 4, 1.0), (3, 2, 0.3), (19, 40, 6.4), (20, 40, 6.4)])
+def test_executables_preconditions_sit_where_the_oracle_puts_them(w, h, sigma):
+    """Vigra's own precondition checks (kernel longer than line; resize source / destination too small), reached through the
+    executable's alg:: functions: the oracle — and the product's plan check, which uses the same rule — must throw on exactly
+    the same shapes, with Vigra's message."""
+    img = np.random.default_rng(w * 100 + h).integers(0, 256, (h, w)).astype(np.float32)
+    theirs = refbin.unit_exception(img, sigma)
+    mine = None
+    for fn in (ol.convolve, ol.reduce, ol.increase):     # the order the helper calls them in
+        try:
+            fn(img, sigma)
+        except ol.OraclePrecondition as e:
+            mine = str(e)
+            break
+    assert (theirs is None) == (mine is None), (theirs, mine)
+    if mine is not None:   # the oracle's unit helpers only name the function that threw; Vigra's text comes from the executable
+        want = {"kernel longer than line": "kernel longer than line", "reduce": "resizeImageNoInterpolation()",
+                "increase": "resizeImageNoInterpolation()"}[mine]
+        assert want in theirs, (theirs, mine)
