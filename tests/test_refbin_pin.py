@@ -12,7 +12,8 @@ Two layers, as in test_ref_pin.py:
      tests/golden/make_refbin_golden.py) — runs everywhere, also where /root/reference does not exist;
   2. the oracle equals the executable run live, stage by stage, on the cases it finishes in seconds, and its alg:: functions
      on random images — runs where the executable and the helper exist.
-The executable is the literal reference (quadratic in the image size): 1080p, the u16 wrap and six octaves stay with oracle/_ref."""
+The executable is the literal reference (quadratic in the image size: config 2 takes it 51 minutes): the six-octave cases stay
+with oracle/_ref."""
 import json
 import os
 
